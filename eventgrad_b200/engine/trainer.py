@@ -1,0 +1,241 @@
+"""Training driver shared by the five reference-equivalent programs.
+
+Reference structure being reproduced (one flat main() per program):
+  epoch loop -> batch loop -> zero_grad / forward / loss / backward
+             -> [communication + consensus average]  -> optimizer.step -> accuracy count
+  then: training time, per-rank event count, final model all-reduce average, total events,
+  rank-0 evaluation of the averaged model
+  (/root/reference/dcifar10/event/event.cpp:245-573, /root/reference/dmnist/cent/cent.cpp:100-214).
+
+What is different by design:
+  * everything after backward() is ONE backend call (fused kernel on the p2p backend);
+  * no host synchronisation inside the step: accuracy / loss / event counters live on the
+    device and are read at epoch boundaries (the reference does 1+3*sz `.item()` per step);
+  * forward+backward (and the fused comm kernel) can be replayed from a CUDA graph.
+"""
+from __future__ import annotations
+
+import time
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from ..config import TrainConfig
+from ..data import BatchLoader, ShardSampler, eval_batches, load_source, per_rank_batch
+from ..models import build_model
+from ..parallel import ParamArena, Ring, make_backend
+from ..utils.ckpt import ckpt_path, load_checkpoint, save_checkpoint
+from ..utils.dist import DistEnv, barrier
+from ..utils.logfiles import RefLogWriter
+from ..utils.timers import PhaseTimer
+
+
+def _compute_dtype(cfg: TrainConfig):
+    return torch.bfloat16 if cfg.dtype == "bf16" else torch.float32
+
+
+class Trainer:
+    def __init__(self, cfg: TrainConfig, env: DistEnv, group=None, train_source=None,
+                 test_source=None):
+        self.cfg, self.env = cfg.validate(), env
+        self.ring = Ring(env.rank, env.world)
+        dev = env.device
+        self.device = dev
+        if cfg.dtype == "tf32" and dev.type == "cuda":
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+        if dev.type == "cuda":
+            torch.backends.cudnn.benchmark = True
+        # identical initial weights on every rank: torch::manual_seed(0) (event.cpp:115)
+        torch.manual_seed(cfg.seed)
+        self.model = build_model(cfg.model, resnet_variant=cfg.resnet_variant)
+        want_p2p = cfg.backend == "p2p" or (cfg.backend == "auto" and dev.type == "cuda")
+        theta_buf = grad_buf = None
+        self._symm = None
+        if want_p2p:
+            from ..parallel.p2p import preallocate_arena_buffers
+            theta_buf, grad_buf, self._symm = preallocate_arena_buffers(self.model, cfg, env, group)
+        self.arena = ParamArena(self.model, dev, theta=theta_buf, grad=grad_buf,
+                                with_momentum=True, channels_last=cfg.channels_last and dev.type == "cuda")
+        if cfg.channels_last and dev.type == "cuda":
+            pass  # activations are produced NHWC by the loader; conv weights already NHWC views
+        self.backend = make_backend(cfg, self.arena, self.ring, env, group) if not want_p2p else \
+            self._make_p2p(group)
+        # ---- data ------------------------------------------------------------------
+        self.train_src = train_source or load_source(cfg.dataset, cfg.data, cfg.train_samples, True)
+        self.test_src = test_source
+        mode = cfg.sampler
+        self.sampler = ShardSampler(len(self.train_src), env.world, env.rank, mode, seed=cfg.seed)
+        self.batch = per_rank_batch(cfg, env.world, self.sampler.local_size)
+        self.loader = BatchLoader(self.train_src, self.sampler, self.batch, dev,
+                                  augment=cfg.augment and cfg.dataset == "cifar10",
+                                  out_dtype=torch.float32, channels_last=cfg.channels_last,
+                                  seed=cfg.seed)
+        self.logw = RefLogWriter(cfg.log_dir, env.rank, cfg.algo, cfg.dataset, bool(cfg.file_write))
+        self.timer = PhaseTimer(dev, enabled=False)
+        self.correct = torch.zeros((), dtype=torch.int64, device=dev)
+        self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+        self.last_loss: Optional[torch.Tensor] = None
+        self.epoch = 0
+        self.steps_done = 0
+        self._graphs = {}
+        self.train_time_s = 0.0
+        if cfg.resume:
+            sd = load_checkpoint(cfg.resume, arena=self.arena, backend=self.backend, model=self.model)
+            self.epoch = int(sd["epoch"])
+        if env.rank == 0 and not cfg.quiet:
+            t = self.arena.table
+            print(f"Number of parameters - {t.n_tensors}", flush=True)       # event.cpp:127-130
+            print(f"Number of elements - {t.n_elems}", flush=True)
+            if cfg.algo == "spevent":
+                print(f"Number of topk elements - {sum(t.topk_counts(cfg.topk_percent))}", flush=True)
+
+    def _make_p2p(self, group):
+        from ..parallel.p2p import P2PBackend
+        return P2PBackend(self.cfg, self.arena, self.ring, self.env, group, symm=self._symm)
+
+    # ------------------------------------------------------------------ one step
+    def _autocast(self):
+        if self.cfg.dtype == "bf16":
+            return torch.autocast(self.device.type, dtype=torch.bfloat16)
+        return torch.autocast(self.device.type, enabled=False)
+
+    def _fwd_bwd(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        with self._autocast():
+            out = self.model(x)
+        loss = F.cross_entropy(out.float(), y)     # == nll_loss(log_softmax(.)) (event.cpp:268,:291)
+        loss.backward()
+        with torch.no_grad():
+            self.correct += (out.argmax(1) == y).sum()
+        return loss.detach()
+
+    def _graphed_fwd_bwd(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        key = tuple(x.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx, sy = x.clone(), y.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):            # warm-up (cudnn autotune, lazy init) off-graph
+                for _ in range(3):
+                    self.arena.zero_grad()
+                    self._fwd_bwd(sx, sy)
+            torch.cuda.current_stream().wait_stream(side)
+            # undo warm-up side effects on counters (BN running stats drift is harmless)
+            self.correct.zero_()
+            self.arena.zero_grad()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sloss = self._fwd_bwd(sx, sy)
+            ent = (g, sx, sy, sloss)
+            self._graphs[key] = ent
+            self.correct.zero_()
+            self.arena.zero_grad()
+        g, sx, sy, sloss = ent
+        sx.copy_(x)
+        sy.copy_(y)
+        g.replay()
+        return sloss
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """zero_grad -> forward -> loss -> backward -> [comm + average + SGD]."""
+        if not getattr(self.backend, "zeroes_grad", False):
+            self.arena.zero_grad()
+        if self.cfg.cuda_graph and self.device.type == "cuda":
+            loss = self._graphed_fwd_bwd(x, y)
+        else:
+            loss = self._fwd_bwd(x, y)
+        self.backend.step()
+        self.steps_done += 1
+        self.last_loss = loss
+        return loss
+
+    # ------------------------------------------------------------------ epochs
+    def fit(self) -> None:
+        cfg, env = self.cfg, self.env
+        barrier(env)
+        t0 = time.perf_counter()
+        stop = False
+        while self.epoch < cfg.epochs and not stop:
+            self.epoch += 1
+            self.model.train()
+            self.correct.zero_()
+            self.sampler.set_epoch(self.epoch - 1)
+            ep_losses = []
+            for x, y in self.loader:
+                loss = self.train_step(x, y)
+                if cfg.file_write:
+                    ep_losses.append((self.backend.pass_num, loss.clone()))
+                if cfg.max_steps and self.steps_done >= cfg.max_steps:
+                    stop = True
+                    break
+            # ---- epoch boundary: the only host syncs of the training loop ----------------
+            acc = 100.0 * float(self.correct.item()) / max(1, self.sampler.local_size)
+            if not cfg.quiet:
+                if cfg.dataset == "mnist":
+                    print(f"{self.epoch}, {acc:g}", flush=True)                       # event.cpp:498
+                else:
+                    print(f"Accuracy in epoch {self.epoch} - {acc:g}", flush=True)     # event.cpp:489
+            self.last_train_acc = acc
+            if cfg.file_write:
+                self.logw.write_steps(self.backend.drain_logs())
+                for pn, l in ep_losses:
+                    self.logw.write_train(pn, float(l))
+                if ep_losses:
+                    self.logw.write_value(self.epoch, float(ep_losses[-1][1]))
+            if cfg.ckpt_dir and cfg.ckpt_every and self.epoch % cfg.ckpt_every == 0:
+                save_checkpoint(ckpt_path(cfg.ckpt_dir, env.rank), epoch=self.epoch, arena=self.arena,
+                                backend=self.backend, model=self.model)
+        self.backend.synchronize()
+        self.train_time_s = time.perf_counter() - t0
+        if env.rank == 0 and not cfg.quiet:
+            print(f"Training time - {self.train_time_s:g}", flush=True)               # event.cpp:495-497
+
+    def finalize(self, evaluate: bool = True) -> dict:
+        """Event statistics, final model averaging, rank-0 test (event.cpp:499-573)."""
+        cfg, env = self.cfg, self.env
+        res = {"rank": env.rank, "train_time_s": self.train_time_s, "steps": self.steps_done}
+        gossip = cfg.algo in ("event", "spevent")
+        if gossip and not cfg.quiet:
+            print(f"No of events in rank {env.rank} - {self.backend.num_events()}", flush=True)
+        res["events_rank"] = self.backend.num_events()
+        res["bytes_sent_rank"] = self.backend.bytes_sent()
+        if cfg.algo != "cent":
+            self.backend.final_average()
+        res["events_total"] = self.backend.total_events() if gossip else 0
+        if gossip and env.rank == 0 and not cfg.quiet:
+            print(f"Total number of events - {res['events_total']}", flush=True)
+        dense = 2 * self.arena.table.n_tensors * self.backend.pass_num * env.world
+        res["dense_messages"] = dense
+        res["messages_saved"] = (1.0 - res["events_total"] / dense) if (gossip and dense) else 0.0
+        if evaluate and env.rank == 0:
+            res.update(self.evaluate())
+        self.logw.close()
+        return res
+
+    @torch.no_grad()
+    def evaluate(self) -> dict:
+        cfg = self.cfg
+        src = self.test_src or load_source(cfg.dataset, cfg.data, cfg.test_samples, False)
+        self.model.eval()
+        # MNIST: the whole test set as one batch (dmnist/event/event.cpp:542-546); CIFAR: 100
+        bs = len(src) if cfg.dataset == "mnist" else cfg.test_batch_size
+        correct, loss_sum, n = 0, 0.0, 0
+        for x, y in eval_batches(src, bs, self.device, channels_last=cfg.channels_last):
+            with self._autocast():
+                out = self.model(x)
+            loss_sum += float(F.cross_entropy(out.float(), y, reduction="sum"))
+            correct += int((out.argmax(1) == y).sum())
+            n += y.numel()
+        acc = 100.0 * correct / max(1, n)
+        if not cfg.quiet:
+            if cfg.dataset == "mnist":
+                print(f"Test loss - {loss_sum / max(1, n):g} ", flush=True)
+            print(f"Num correct - {correct}", flush=True)
+            print(f"Test Accuracy - {acc:g}", flush=True)
+        self.model.train()
+        return {"test_correct": correct, "test_acc": acc, "test_loss": loss_sum / max(1, n)}
+
+    def close(self) -> None:
+        self.backend.close()
