@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""Headline benchmark (driver contract).
+
+Metric (BASELINE.json): images/sec, whole job, device-timed, max over ranks, for the CIFAR-10
+ResNet D-PSGD training step -- the dcifar10/event configuration of the reference
+(/root/reference/dcifar10/event/event.cpp:29-42, :91, :196-200): ResNet{2,2,2,2} exactly as the
+reference builds it (12 BasicBlocks, 86 tensors, 17 444 682 parameters), GLOBAL batch 256 split
+over the ranks (strong scaling), SGD lr 1e-2 momentum 0.9, ring gossip with both neighbours every
+step.  Default algorithm = dense D-PSGD (every tensor pushed every step -- the most communication
+the reference ever does); `--algo event|spevent|cent` times the other programs.
+
+    python bench.py --gpus N --steps K --warmup W         (torchrun launches N ranks for N>1)
+
+One JSON line on rank 0.  `value` is timed on the device (CUDA events) over K whole training steps
+(forward, backward, fused exchange+average+SGD) with inputs already resident; `e2e` repeats the
+measurement through the public Trainer API with, every step, the H2D copy of that step's uint8
+batch from pinned host memory, GPU decode/augmentation, and a D2H read of the loss.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    p.add_argument("--algo", default="dpsgd", choices=["dpsgd", "event", "spevent", "cent"])
+    p.add_argument("--model", default="resnet18")
+    p.add_argument("--global-batch", type=int, default=256)
+    p.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "tf32"])
+    p.add_argument("--sync-mode", default="iter", choices=["iter", "async"])
+    p.add_argument("--horizon", type=float, default=1.0)
+    p.add_argument("--topk", type=float, default=10.0)
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--no-channels-last", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--out", default="")
+    return p.parse_args()
+
+
+def reference_arm(args):
+    # The reference is five C++ main() programs (LibTorch + MPI + OpenCV C++), with no setup.py /
+    # pyproject: `pip install --no-index ... /root/reference` fails ("not installable"), and the
+    # image has no MPI (mpi.h / mpirun), no OpenCV C++ headers and no datasets. See DESIGN.md.
+    print(json.dumps({"impl": "reference",
+                      "unavailable": "reference is not pip-installable (no setup.py/pyproject; C++ mains "
+                                     "need MPI + OpenCV C++ + dataset files, none present offline)"}))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.nn.functional as F
+    from eventgrad_b200.config import preset
+    from eventgrad_b200.data import synthetic_source
+    from eventgrad_b200.engine.trainer import Trainer
+    from eventgrad_b200.utils.clocks import ClockSampler
+    from eventgrad_b200.utils.dist import barrier, init_distributed, max_over_ranks, shutdown, sum_over_ranks
+
+    env = init_distributed("cuda")
+    N = env.world
+    if N != args.gpus and env.rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={N}", file=sys.stderr)
+    gb = args.global_batch if args.scaling == "strong" else args.global_batch * N
+    per_rank = max(1, gb // N)
+    algo = {"dpsgd": "decent", "event": "event", "spevent": "spevent", "cent": "cent"}[args.algo]
+    backend = "p2p" if args.impl == "ours" else "nccl"
+    steps_needed = args.warmup + args.steps + 2
+    n_train = max(per_rank * N * 8, 4096)
+    cfg = preset("cifar_event", algo=algo, model=args.model, backend=backend, device="cuda",
+                 dtype=args.dtype, batch_size=gb, batch_mode="global", epochs=10 ** 6,
+                 sync_mode="iter" if algo == "decent" else args.sync_mode,
+                 horizon=args.horizon, topk_percent=args.topk,
+                 channels_last=not args.no_channels_last, cuda_graph=not args.no_graph,
+                 train_samples=n_train, test_samples=256, quiet=True, augment=True)
+    src = synthetic_source("cifar10", n_train).pin()
+    tr = Trainer(cfg, env, train_source=src)
+    dev = env.device
+    table = tr.arena.table
+
+    # ---------------- device-timed: inputs resident on the GPU (a rotating pool of batches) -------
+    pool = []
+    it = iter(tr.loader)
+    for _ in range(4):
+        x, y = next(it)
+        pool.append((x.clone(), y.clone()))
+    torch.cuda.synchronize()
+    for i in range(args.warmup):
+        tr.train_step(*pool[i % len(pool)])
+    torch.cuda.synchronize()
+    barrier(env)
+    sampler = ClockSampler(dev.index or 0, 100).start() if env.rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(env)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        tr.train_step(*pool[i % len(pool)])
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(env)
+    ms = max_over_ranks(e0.elapsed_time(e1), env)
+    clocks = sampler.stop() if sampler is not None else None
+    tr.backend.check_status() if hasattr(tr.backend, "check_status") else None
+    ms_per_step = ms / args.steps
+    value = gb * args.steps / (ms / 1e3)
+    loss_dev = float(tr.last_loss)
+
+    # ---------------- end to end through the public API: H2D every step + D2H loss every step ----
+    e2e = None
+    if not args.no_e2e:
+        it = iter(tr.loader)
+        for _ in range(args.warmup):
+            x, y = next(it)
+            tr.train_step(x, y)
+        torch.cuda.synchronize()
+        barrier(env)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        d2h = 0
+        for _ in range(args.steps):
+            try:
+                x, y = next(it)
+            except StopIteration:
+                it = iter(tr.loader)
+                x, y = next(it)
+            loss = tr.train_step(x, y)
+            lv = loss.item()                      # D2H read of the step result
+            d2h += loss.element_size()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier(env)
+        ms2 = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3), env)
+        c, h, w = src.sample_shape
+        e2e = {"value": gb * args.steps / (ms2 / 1e3), "unit": "images/s",
+               "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": int(per_rank * (c * h * w + 8) * N),
+               "d2h_bytes_per_step": int(d2h / args.steps * N),
+               "last_loss": lv}
+
+    # ---------------- communication accounting ----------------------------------------------------
+    be = tr.backend
+    total_steps = be.pass_num
+    bytes_rank = be.bytes_sent()
+    bytes_all = sum_over_ranks(bytes_rank, env)
+    events_all = sum_over_ranks(be.num_events(), env)
+    dense_msgs = 2 * table.n_tensors * total_steps * N
+    push_bytes_step = bytes_rank / max(1, total_steps)
+    kern_per_step = {"decent": 1, "event": 1, "cent": 1, "spevent": 11}[algo]
+    out = {
+        "metric": "images/sec, CIFAR-10 ResNet (reference topology) D-PSGD ring gossip training step",
+        "value": value, "unit": "images/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "impl": args.impl,
+        "config": {"model": f"{args.model}-ref(12 BasicBlocks, 86 tensors, {table.n_elems} params)"
+                            if args.model == "resnet18" else args.model,
+                   "global_batch": gb, "per_gpu_batch": per_rank, "image": "3x32x32",
+                   "parallelism": f"dp{N}-ring-gossip" if algo != "cent" else f"dp{N}-allreduce",
+                   "algorithm": args.algo, "backend": backend, "sync_mode": cfg.sync_mode,
+                   "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": cfg.cuda_graph,
+                   "channels_last": cfg.channels_last,
+                   "l2_policy": "per-step working set (theta,grad,mom,2 inboxes = "
+                                f"{5 * table.n_padded * 4 / 1e6:.0f} MB + activations) exceeds the 126 MB L2; "
+                                "no explicit flush"},
+        "gpu_launches": int(kern_per_step * args.steps) if args.impl == "ours" else 0,
+        "own_kernels_per_step": kern_per_step if args.impl == "ours" else 0,
+        "comm": {"bytes_pushed_per_step_per_gpu": push_bytes_step,
+                 "events_total": events_all, "dense_messages": dense_msgs,
+                 "messages_saved": (1.0 - events_all / dense_msgs) if (algo in ("event", "spevent") and dense_msgs and N > 1) else 0.0,
+                 "bytes_pushed_total": bytes_all},
+        "loss": loss_dev,
+    }
+    if clocks is not None:
+        out["clocks"] = clocks
+    if e2e is not None:
+        out["e2e"] = e2e
+    if env.rank == 0:
+        line = json.dumps(out)
+        print(line, flush=True)
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+    tr.close()
+    shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,181 @@
+// eventgrad_b200 -- host-visible launch API of the sm_100a kernels.
+// Pure CUDA (no torch headers) so the .cu files compile in seconds; bindings.cpp adapts tensors.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define EG_TILE 2048     // fp32 elements per tile == parallel/arena.py:TILE
+#define EG_THREADS 256
+
+namespace egb {
+
+// ------------------------------------------------------------------ tensor table (device)
+struct TableDev {
+  const int* tile_tensor;   // [n_tiles]  tile -> parameter tensor
+  const int* t_tile_start;  // [n_tensors]
+  const int* t_tile_count;  // [n_tensors]
+  const int* t_numel;       // [n_tensors]
+  const int* t_msg_bytes;   // [n_tensors] bytes one neighbour receives when tensor i fires
+  int n_tiles;
+  int n_tensors;
+};
+
+// ------------------------------------------------------------------ event-trigger FSM (device)
+// Mirrors /root/reference/dcifar10/event/event.cpp:300-365 -- see parallel/trigger.py (oracle).
+struct FsmDev {
+  float* thres;        // [sz]
+  float* last_norm;    // [sz]
+  float* last_iter;    // [sz]
+  float* slopes;       // [sz * history]
+  int* fire;           // [sz] decision for the step that is about to run
+  float* cur_norm;     // [sz] sender norm used for that decision
+  unsigned long long* counters;  // [0] events (+2 per fire)  [1] payload bytes pushed  [2] fired tensors
+  int* pass_num;       // completed steps (device-resident so CUDA graphs can replay the step)
+  float* log_ring;     // optional [log_cap][sz][5] = norm, thres, fired, left_norm, right_norm
+  int log_cap;
+  float horizon;
+  float constant;
+  int thres_type;      // 1 adaptive, 0 constant
+  int history;         // sent_history (<= 8)
+  int initial_comm_passes;
+  int enabled;         // 0: decent / cent (no trigger: fire[] stays all-ones)
+};
+
+// ------------------------------------------------------------------ fused gossip step
+// One launch = push theta_k to both ring neighbours (only tensors whose trigger fired) ->
+// [iter-sync: flag handshake] -> (theta+L+R)/3 -> SGD(+momentum) -> write theta_{k+1} (+bf16
+// shadow, zero grad) accumulating per-warp sum-of-squares -> last CTA evaluates the trigger FSM
+// for step k+1 from those partials.  Replaces, per step, 86x{norm.item(), 2 MPI_Put, 2 memcpy,
+// add_, add_, div_} + optimizer.step() of the reference.
+struct GossipParams {
+  float* theta;
+  float* grad;
+  float* mom;               // may be null when mu == 0
+  const float* inbox_l;     // local: what my LEFT neighbour last pushed (or its sparse replica)
+  const float* inbox_r;
+  float* push_l;            // peer-mapped: LEFT neighbour's inbox_r
+  float* push_r;            // peer-mapped: RIGHT neighbour's inbox_l
+  __nv_bfloat16* shadow;    // optional bf16 copy of theta_{k+1} for the next forward
+  float* tile_ss;           // [n_tiles * 8] per-warp sum theta_{k+1}^2
+  float* tile_ss_l;         // optional (logging): sum inbox_l^2
+  float* tile_ss_r;
+  // iter-sync handshake (all monotonic step counters)
+  uint32_t* flag_from_l;    // local, written by left neighbour   [n_groups * grid]
+  uint32_t* flag_from_r;
+  uint32_t* flag_to_l;      // peer-mapped: left neighbour's flag_from_r
+  uint32_t* flag_to_r;      // peer-mapped: right neighbour's flag_from_l
+  uint32_t* ack_from_l;     // local: left neighbour finished reading what I pushed at step k
+  uint32_t* ack_from_r;
+  uint32_t* ack_to_l;       // peer-mapped
+  uint32_t* ack_to_r;
+  unsigned int* ticket;     // last-CTA election
+  int* status;              // sticky error word
+  unsigned long long timeout_ns;
+  TableDev tab;
+  FsmDev fsm;
+  float lr;
+  float mu;
+  int do_mix;               // 0: plain SGD (serial run)
+  int do_push;              // 0: sparse mode (records are pushed by the top-k kernels) / serial
+  int sync;                 // 1: iter-sync handshake, 0: async (reference RMA semantics)
+  int send_ack;             // sync: write acks in the tail (0 when another kernel acks)
+  int zero_grad;
+  int group_iters;          // tiles per CTA between two flag publications (sync)
+  int vec256_push;          // 1: 256-bit peer stores, 0: 2x128-bit
+};
+
+int gossip_max_grid(int device);  // co-resident CTAs (persistent grid upper bound)
+cudaError_t launch_gossip_step(const GossipParams& p, int grid, cudaStream_t s);
+// (re)compute tile_ss (+ shadow) from theta and evaluate the trigger for step pass_num+1.
+cudaError_t launch_gossip_init(const GossipParams& p, int grid, int run_fsm, cudaStream_t s);
+// Trigger FSM alone with externally supplied norms (unit tests against the oracle).
+cudaError_t launch_fsm_decide(const FsmDev& f, const TableDev& t, const float* ext_norm, cudaStream_t s);
+
+// ------------------------------------------------------------------ one-/two-shot all-reduce
+// cent: grad <- sum_r grad_r / R fused with the SGD step; also final parameter averaging.
+struct AllReduceParams {
+  float* const* peer_bufs;  // device array [world] of peer-mapped pointers to the SAME buffer on each rank
+  float* local;             // == peer_bufs[rank]
+  float* theta;             // SGD mode: parameters (may alias nothing in `local`)
+  float* mom;
+  __nv_bfloat16* shadow;
+  uint32_t* const* peer_flags;  // device array [world]: each rank's flag block (peer-mapped)
+  uint32_t* flags;              // local flag block: [3][grid][world]
+  unsigned int* ticket;
+  int* status;
+  int* step_ctr;            // device-resident launch counter for the flag protocol
+  unsigned long long timeout_ns;
+  int n_tiles;
+  int rank;
+  int world;
+  float lr;
+  float mu;
+  int mode;                 // 0: average in place   1: average + SGD (+ zero grad)
+  int two_shot;             // 0: every rank reads all peers   1: reduce-scatter + broadcast
+  int zero_after;
+};
+cudaError_t launch_allreduce(const AllReduceParams& p, int grid, cudaStream_t s);
+
+// ------------------------------------------------------------------ sparse (top-k) exchange
+struct SparseParams {
+  const float* theta;
+  float* prev;              // what this rank last sent (element-wise)
+  float* rep_l;             // persistent replicas of the neighbours
+  float* rep_r;
+  // records: per tensor [vals(k_i) | idx(k_i)] at rec_off[i] (4-byte words)
+  const float* rec_from_l;  // local inbox records written by neighbours
+  const float* rec_from_r;
+  float* rec_to_l;          // peer-mapped: left neighbour's rec_from_r
+  float* rec_to_r;          // peer-mapped: right neighbour's rec_from_l
+  uint32_t* seq_from_l;     // [sz] local: step at which the record of tensor i was last rewritten
+  uint32_t* seq_from_r;
+  uint32_t* seq_to_l;       // peer-mapped
+  uint32_t* seq_to_r;
+  uint32_t* applied_l;      // [sz] local bookkeeping: last seq applied to the replica
+  uint32_t* applied_r;
+  uint32_t* done_from_l;    // sync: neighbour finished writing all records of step k
+  uint32_t* done_from_r;
+  uint32_t* done_to_l;
+  uint32_t* done_to_r;
+  uint32_t* ack_from_l;
+  uint32_t* ack_from_r;
+  uint32_t* ack_to_l;
+  uint32_t* ack_to_r;
+  const int* t_k;           // [sz] k_i
+  const int* t_rec_off;     // [sz] record offset (words)
+  // scratch
+  unsigned int* hist;       // [sz][2048]
+  unsigned int* sel_prefix; // [sz] radix prefix of the k-th largest |diff| found so far
+  unsigned int* sel_remain; // [sz] rank still to resolve inside the prefix bucket
+  unsigned int* tile_gt;    // [n_tiles] elements > tau in the tile
+  unsigned int* tile_eq;    // [n_tiles] elements == tau
+  unsigned int* t_gt_total; // [sz]
+  const int* fire;
+  const int* pass_num;
+  unsigned int* ticket;
+  int* status;
+  unsigned long long timeout_ns;
+  TableDev tab;
+  int sync;
+};
+cudaError_t launch_sparse_select_push(const SparseParams& p, int grid, cudaStream_t s);
+cudaError_t launch_sparse_apply(const SparseParams& p, int grid, cudaStream_t s);
+
+// ------------------------------------------------------------------ data path
+// uint8 NCHW batch -> normalised fp32/bf16 (NCHW or NHWC) with pad+flip+crop folded in.
+cudaError_t launch_decode_augment(const uint8_t* in, void* out, const int* oy, const int* ox,
+                                  const int* flip, int B, int C, int H, int W, int pad, float scale,
+                                  float mean, float inv_std, int out_bf16, int nhwc, cudaStream_t s);
+
+// ------------------------------------------------------------------ IPC window runtime
+// The RMA-window replacement (MPI_Alloc_mem + MPI_Win_create, event.cpp:138-147).
+struct IpcHandle {
+  unsigned char bytes[64];
+};
+cudaError_t ipc_alloc(size_t nbytes, void** ptr, IpcHandle* h);
+cudaError_t ipc_open(const IpcHandle& h, void** ptr);
+cudaError_t ipc_close(void* ptr);
+cudaError_t ipc_free(void* ptr);
+
+}  // namespace egb

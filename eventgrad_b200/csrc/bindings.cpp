@@ -1,0 +1,176 @@
+// eventgrad_b200 -- Python bindings (pybind11 + CUDA runtime only; no torch headers, so the
+// whole extension rebuilds in seconds and carries no libtorch ABI coupling).  Tensors cross the
+// boundary as raw device addresses (tensor.data_ptr()); streams as torch's cuda_stream handle.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+
+#include "api.h"
+
+namespace py = pybind11;
+using namespace egb;
+
+static void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <class S>
+using Setter = std::function<void(S&, py::object)>;
+
+#define PTRF(S, f) \
+  { #f, [](S& p, py::object v) { p.f = reinterpret_cast<decltype(p.f)>(v.cast<uintptr_t>()); } }
+#define NUMF(S, f) \
+  { #f, [](S& p, py::object v) { p.f = v.cast<decltype(p.f)>(); } }
+#define PTRF2(S, sub, f) \
+  { #sub "." #f, [](S& p, py::object v) { p.sub.f = reinterpret_cast<decltype(p.sub.f)>(v.cast<uintptr_t>()); } }
+#define NUMF2(S, sub, f) \
+  { #sub "." #f, [](S& p, py::object v) { p.sub.f = v.cast<decltype(p.sub.f)>(); } }
+
+#define TAB_FIELDS(S)                                                                              \
+  PTRF2(S, tab, tile_tensor), PTRF2(S, tab, t_tile_start), PTRF2(S, tab, t_tile_count),            \
+      PTRF2(S, tab, t_numel), PTRF2(S, tab, t_msg_bytes), NUMF2(S, tab, n_tiles), NUMF2(S, tab, n_tensors)
+
+static const std::unordered_map<std::string, Setter<GossipParams>> kGossip = {
+    PTRF(GossipParams, theta), PTRF(GossipParams, grad), PTRF(GossipParams, mom),
+    PTRF(GossipParams, inbox_l), PTRF(GossipParams, inbox_r), PTRF(GossipParams, push_l),
+    PTRF(GossipParams, push_r), PTRF(GossipParams, shadow), PTRF(GossipParams, tile_ss),
+    PTRF(GossipParams, tile_ss_l), PTRF(GossipParams, tile_ss_r), PTRF(GossipParams, flag_from_l),
+    PTRF(GossipParams, flag_from_r), PTRF(GossipParams, flag_to_l), PTRF(GossipParams, flag_to_r),
+    PTRF(GossipParams, ack_from_l), PTRF(GossipParams, ack_from_r), PTRF(GossipParams, ack_to_l),
+    PTRF(GossipParams, ack_to_r), PTRF(GossipParams, ticket), PTRF(GossipParams, status),
+    NUMF(GossipParams, timeout_ns), NUMF(GossipParams, lr), NUMF(GossipParams, mu),
+    NUMF(GossipParams, do_mix), NUMF(GossipParams, do_push), NUMF(GossipParams, sync),
+    NUMF(GossipParams, send_ack), NUMF(GossipParams, zero_grad), NUMF(GossipParams, group_iters),
+    NUMF(GossipParams, vec256_push), TAB_FIELDS(GossipParams),
+    PTRF2(GossipParams, fsm, thres), PTRF2(GossipParams, fsm, last_norm), PTRF2(GossipParams, fsm, last_iter),
+    PTRF2(GossipParams, fsm, slopes), PTRF2(GossipParams, fsm, fire), PTRF2(GossipParams, fsm, cur_norm),
+    PTRF2(GossipParams, fsm, counters), PTRF2(GossipParams, fsm, pass_num), PTRF2(GossipParams, fsm, log_ring),
+    NUMF2(GossipParams, fsm, log_cap), NUMF2(GossipParams, fsm, horizon), NUMF2(GossipParams, fsm, constant),
+    NUMF2(GossipParams, fsm, thres_type), NUMF2(GossipParams, fsm, history),
+    NUMF2(GossipParams, fsm, initial_comm_passes), NUMF2(GossipParams, fsm, enabled),
+};
+
+static const std::unordered_map<std::string, Setter<AllReduceParams>> kAllReduce = {
+    PTRF(AllReduceParams, peer_bufs), PTRF(AllReduceParams, local), PTRF(AllReduceParams, theta),
+    PTRF(AllReduceParams, mom), PTRF(AllReduceParams, shadow), PTRF(AllReduceParams, peer_flags),
+    PTRF(AllReduceParams, flags), PTRF(AllReduceParams, ticket), PTRF(AllReduceParams, status),
+    PTRF(AllReduceParams, step_ctr), NUMF(AllReduceParams, timeout_ns), NUMF(AllReduceParams, n_tiles),
+    NUMF(AllReduceParams, rank), NUMF(AllReduceParams, world), NUMF(AllReduceParams, lr),
+    NUMF(AllReduceParams, mu), NUMF(AllReduceParams, mode), NUMF(AllReduceParams, two_shot),
+    NUMF(AllReduceParams, zero_after),
+};
+
+static const std::unordered_map<std::string, Setter<SparseParams>> kSparse = {
+    PTRF(SparseParams, theta), PTRF(SparseParams, prev), PTRF(SparseParams, rep_l), PTRF(SparseParams, rep_r),
+    PTRF(SparseParams, rec_from_l), PTRF(SparseParams, rec_from_r), PTRF(SparseParams, rec_to_l),
+    PTRF(SparseParams, rec_to_r), PTRF(SparseParams, seq_from_l), PTRF(SparseParams, seq_from_r),
+    PTRF(SparseParams, seq_to_l), PTRF(SparseParams, seq_to_r), PTRF(SparseParams, applied_l),
+    PTRF(SparseParams, applied_r), PTRF(SparseParams, done_from_l), PTRF(SparseParams, done_from_r),
+    PTRF(SparseParams, done_to_l), PTRF(SparseParams, done_to_r), PTRF(SparseParams, ack_from_l),
+    PTRF(SparseParams, ack_from_r), PTRF(SparseParams, ack_to_l), PTRF(SparseParams, ack_to_r),
+    PTRF(SparseParams, t_k), PTRF(SparseParams, t_rec_off), PTRF(SparseParams, hist),
+    PTRF(SparseParams, sel_prefix), PTRF(SparseParams, sel_remain), PTRF(SparseParams, tile_gt),
+    PTRF(SparseParams, tile_eq), PTRF(SparseParams, t_gt_total), PTRF(SparseParams, fire),
+    PTRF(SparseParams, pass_num), PTRF(SparseParams, ticket), PTRF(SparseParams, status),
+    NUMF(SparseParams, timeout_ns), NUMF(SparseParams, sync), TAB_FIELDS(SparseParams),
+};
+
+template <class S>
+static void bind_params(py::module_& m, const char* name, const std::unordered_map<std::string, Setter<S>>& tbl) {
+  py::class_<S>(m, name)
+      .def(py::init([]() {
+        S p;
+        std::memset(&p, 0, sizeof(S));
+        return p;
+      }))
+      .def("set",
+           [&tbl](S& p, const std::string& k, py::object v) {
+             auto it = tbl.find(k);
+             if (it == tbl.end()) throw std::invalid_argument("unknown field " + k);
+             it->second(p, v);
+           })
+      .def("update",
+           [&tbl](S& p, py::dict d) {
+             for (auto kv : d) {
+               const std::string k = kv.first.cast<std::string>();
+               auto it = tbl.find(k);
+               if (it == tbl.end()) throw std::invalid_argument("unknown field " + k);
+               it->second(p, py::reinterpret_borrow<py::object>(kv.second));
+             }
+           })
+      .def_static("fields", [&tbl]() {
+        std::vector<std::string> v;
+        for (auto& kv : tbl) v.push_back(kv.first);
+        return v;
+      });
+}
+
+static cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "eventgrad_b200 sm_100a kernels";
+  m.attr("TILE") = EG_TILE;
+  m.attr("arch") = "sm_100a";
+  bind_params<GossipParams>(m, "GossipParams", kGossip);
+  bind_params<AllReduceParams>(m, "AllReduceParams", kAllReduce);
+  bind_params<SparseParams>(m, "SparseParams", kSparse);
+
+  m.def("gossip_max_grid", &gossip_max_grid);
+  m.def("gossip_step", [](const GossipParams& p, int grid, uintptr_t s) {
+    check(launch_gossip_step(p, grid, S(s)), "gossip_step");
+  });
+  m.def("gossip_init", [](const GossipParams& p, int grid, int run_fsm, uintptr_t s) {
+    check(launch_gossip_init(p, grid, run_fsm, S(s)), "gossip_init");
+  });
+  m.def("fsm_decide", [](const GossipParams& p, uintptr_t ext_norm, uintptr_t s) {
+    check(launch_fsm_decide(p.fsm, p.tab, reinterpret_cast<const float*>(ext_norm), S(s)), "fsm_decide");
+  });
+  m.def("allreduce", [](const AllReduceParams& p, int grid, uintptr_t s) {
+    check(launch_allreduce(p, grid, S(s)), "allreduce");
+  });
+  m.def("sparse_select_push", [](const SparseParams& p, int grid, uintptr_t s) {
+    check(launch_sparse_select_push(p, grid, S(s)), "sparse_select_push");
+  });
+  m.def("sparse_apply", [](const SparseParams& p, int grid, uintptr_t s) {
+    check(launch_sparse_apply(p, grid, S(s)), "sparse_apply");
+  });
+  m.def("decode_augment",
+        [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,
+           int pad, float scale, float mean, float inv_std, int out_bf16, int nhwc, uintptr_t s) {
+          check(launch_decode_augment(reinterpret_cast<const uint8_t*>(in), reinterpret_cast<void*>(out),
+                                      reinterpret_cast<const int*>(oy), reinterpret_cast<const int*>(ox),
+                                      reinterpret_cast<const int*>(flip), B, C, H, W, pad, scale, mean,
+                                      inv_std, out_bf16, nhwc, S(s)),
+                "decode_augment");
+        });
+
+  // ---- IPC window runtime -------------------------------------------------------------------
+  m.def("ipc_alloc", [](size_t nbytes) {
+    void* ptr = nullptr;
+    IpcHandle h;
+    check(ipc_alloc(nbytes, &ptr, &h), "ipc_alloc");
+    return py::make_tuple(reinterpret_cast<uintptr_t>(ptr),
+                          py::bytes(reinterpret_cast<const char*>(h.bytes), sizeof(h.bytes)));
+  });
+  m.def("ipc_open", [](py::bytes hb) {
+    std::string s = hb;
+    if (s.size() != sizeof(IpcHandle)) throw std::invalid_argument("bad IPC handle size");
+    IpcHandle h;
+    std::memcpy(h.bytes, s.data(), sizeof(h.bytes));
+    void* ptr = nullptr;
+    check(ipc_open(h, &ptr), "ipc_open");
+    return reinterpret_cast<uintptr_t>(ptr);
+  });
+  m.def("ipc_close", [](uintptr_t p) { check(ipc_close(reinterpret_cast<void*>(p)), "ipc_close"); });
+  m.def("ipc_free", [](uintptr_t p) { check(ipc_free(reinterpret_cast<void*>(p)), "ipc_free"); });
+  m.def("device_can_access_peer", [](int dev, int peer) {
+    int ok = 0;
+    check(cudaDeviceCanAccessPeer(&ok, dev, peer), "cudaDeviceCanAccessPeer");
+    return ok != 0;
+  });
+}

@@ -1,0 +1,348 @@
+// eventgrad_b200 -- fused event-triggered gossip step (K1/K2) for sm_100a.
+//
+// What one launch does on every rank (persistent grid, one tile of EG_TILE floats per CTA
+// iteration):
+//   1. push   : tiles of tensors whose trigger fired are stored straight into the LEFT
+//               neighbour's "from-right" inbox and the RIGHT neighbour's "from-left" inbox
+//               (peer-mapped pointers -> NVLink 5 / NVSwitch).  Below threshold nothing is
+//               stored, so link bytes scale with events (MPI_Put semantics,
+//               /root/reference/dcifar10/event/event.cpp:317-332).
+//   2. sync   : iter mode publishes one release-flag per (CTA, tile group) and waits for the
+//               two neighbours' matching flags, so exchange and math overlap group by group;
+//               async mode reads whatever the inboxes hold (reference: unsynchronised window
+//               reads, event.cpp:372-374).
+//   3. mix+opt: theta <- ((theta+L)+R)/3 ; m <- mu*m+g ; theta <- theta - lr*m   (event.cpp:
+//               459-461, :479), rounding identical to add_/add_/div_/SGD.
+//   4. norm-on-write: per-warp sum theta_new^2 partials; the last CTA reduces them per tensor
+//               in fixed order and runs the trigger FSM for the NEXT step (event.cpp:300-355),
+//               so the step needs no extra pass over theta, no grid sync and no host sync.
+#include "api.h"
+#include "common.cuh"
+
+namespace egb {
+
+// -------------------------------------------------------------------------------------------
+// Trigger FSM for step `next_step`, executed by ONE CTA (8 warps, one tensor per warp turn).
+// -------------------------------------------------------------------------------------------
+__device__ void fsm_decide(const FsmDev& f, const TableDev& tab, const float* tile_ss,
+                           const float* tile_ss_l, const float* tile_ss_r, const float* ext_norm,
+                           int next_step) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sz = tab.n_tensors;
+  float* row_next = nullptr;   // log row of the decision (step next_step)
+  float* row_cur = nullptr;    // log row of the step that just ran (receive-side norms)
+  if (f.log_ring != nullptr && f.log_cap > 0) {
+    row_next = f.log_ring + (size_t)((next_step - 1) % f.log_cap) * sz * 5;
+    if (next_step >= 2) row_cur = f.log_ring + (size_t)((next_step - 2) % f.log_cap) * sz * 5;
+  }
+  for (int i = warp; i < sz; i += EG_WARPS) {
+    const int ts = tab.t_tile_start[i], tc = tab.t_tile_count[i];
+    double acc = 0.0, accl = 0.0, accr = 0.0;
+    if (ext_norm == nullptr) {
+      const int beg = ts * EG_WARPS, end = (ts + tc) * EG_WARPS;
+      for (int j = beg + lane; j < end; j += 32) {
+        acc += (double)__ldcg(tile_ss + j);
+        if (row_cur != nullptr && tile_ss_l != nullptr) {
+          accl += (double)__ldcg(tile_ss_l + j);
+          accr += (double)__ldcg(tile_ss_r + j);
+        }
+      }
+      acc = warp_sum_d(acc);
+      accl = warp_sum_d(accl);
+      accr = warp_sum_d(accr);
+    }
+    if (lane == 0) {
+      const float norm = ext_norm ? ext_norm[i] : (float)sqrt(acc);
+      if (row_cur != nullptr && tile_ss_l != nullptr) {
+        row_cur[i * 5 + 3] = (float)sqrt(accl);
+        row_cur[i * 5 + 4] = (float)sqrt(accr);
+      }
+      f.cur_norm[i] = norm;
+      if (f.enabled) {
+        const float value_diff = fabsf(__fsub_rn(norm, f.last_norm[i]));
+        const float iter_diff = __fsub_rn((float)next_step, f.last_iter[i]);
+        float th = (f.thres_type == 1) ? __fmul_rn(f.thres[i], f.horizon) : f.constant;
+        const bool fire = (value_diff >= th) || (next_step < f.initial_comm_passes);
+        if (row_next != nullptr) {
+          row_next[i * 5 + 0] = norm;
+          row_next[i * 5 + 1] = th;
+          row_next[i * 5 + 2] = fire ? 1.f : 0.f;
+        }
+        if (fire) {
+          const int H = f.history;
+          float* sl = f.slopes + (size_t)i * H;
+          double avg = 0.0;
+          for (int j = 0; j < H - 1; ++j) {
+            sl[j] = sl[j + 1];
+            avg += (double)sl[j];
+          }
+          sl[H - 1] = __fdiv_rn(value_diff, iter_diff);
+          avg += (double)sl[H - 1];
+          avg /= (double)H;
+          if (f.thres_type == 1) th = (float)avg;
+          f.last_norm[i] = norm;
+          f.last_iter[i] = (float)next_step;
+        }
+        f.thres[i] = th;
+        f.fire[i] = fire ? 1 : 0;
+      }
+    }
+  }
+}
+
+// Account the messages of the step that just ran: +2 events per fired tensor (one per ring
+// neighbour, event.cpp:319) and the payload bytes that crossed NVLink.
+__device__ void count_events(const FsmDev& f, const TableDev& tab) {
+  if (!f.enabled) return;
+  unsigned long long ev = 0, by = 0, nf = 0;
+  for (int i = threadIdx.x; i < tab.n_tensors; i += EG_THREADS) {
+    if (f.fire[i]) {
+      ev += 2;
+      by += 2ull * (unsigned long long)tab.t_msg_bytes[i];
+      nf += 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ev += __shfl_xor_sync(0xffffffffu, ev, o);
+    by += __shfl_xor_sync(0xffffffffu, by, o);
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if ((threadIdx.x & 31) == 0 && ev) {
+    atomicAdd(f.counters + 0, ev);
+    atomicAdd(f.counters + 1, by);
+    atomicAdd(f.counters + 2, nf);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_tile(const GossipParams& p, size_t base, const F8& th) {
+  if (p.vec256_push) {
+    st_f8(p.push_l + base, th);
+    st_f8(p.push_r + base, th);
+  } else {
+    st_f8_v4(p.push_l + base, th);
+    st_f8_v4(p.push_r + base, th);
+  }
+}
+
+// mix + SGD + norm-on-write for one tile. `th` already holds theta_k for this thread's 8 floats.
+template <bool kMom>
+__device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t base, F8 th, int lane,
+                                         int warp) {
+  const bool logrecv = (p.tile_ss_l != nullptr);
+  float ssl = 0.f, ssr = 0.f;
+  if (p.do_mix) {
+    const F8 L = ld_f8_cg(p.inbox_l + base);
+    const F8 R = ld_f8_cg(p.inbox_r + base);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      th.v[e] = __fdiv_rn(__fadd_rn(__fadd_rn(th.v[e], L.v[e]), R.v[e]), 3.0f);
+      if (logrecv) {
+        ssl = __fmaf_rn(L.v[e], L.v[e], ssl);
+        ssr = __fmaf_rn(R.v[e], R.v[e], ssr);
+      }
+    }
+  }
+  const F8 g = ld_f8(p.grad + base);
+  float ss = 0.f;
+  if (kMom) {
+    F8 m = ld_f8(p.mom + base);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      m.v[e] = __fadd_rn(__fmul_rn(m.v[e], p.mu), g.v[e]);
+      th.v[e] = __fmaf_rn(m.v[e], -p.lr, th.v[e]);
+      ss = __fmaf_rn(th.v[e], th.v[e], ss);
+    }
+    st_f8(p.mom + base, m);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      th.v[e] = __fmaf_rn(g.v[e], -p.lr, th.v[e]);
+      ss = __fmaf_rn(th.v[e], th.v[e], ss);
+    }
+  }
+  st_f8(p.theta + base, th);
+  if (p.shadow != nullptr) st_bf16x8(p.shadow + base, th);
+  if (p.zero_grad) {
+    F8 z;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) z.v[e] = 0.f;
+    st_f8(p.grad + base, z);
+  }
+  ss = warp_sum(ss);
+  if (logrecv) {
+    ssl = warp_sum(ssl);
+    ssr = warp_sum(ssr);
+  }
+  if (lane == 0) {
+    p.tile_ss[(size_t)t * EG_WARPS + warp] = ss;
+    if (logrecv) {
+      p.tile_ss_l[(size_t)t * EG_WARPS + warp] = ssl;
+      p.tile_ss_r[(size_t)t * EG_WARPS + warp] = ssr;
+    }
+  }
+}
+
+// Elect the last CTA of the grid; it runs the FSM for step+1, acks, and bumps the step counter.
+__device__ __forceinline__ void grid_tail(const GossipParams& p, int step) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(p.ticket, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (p.do_mix) count_events(p.fsm, p.tab);
+  __syncthreads();
+  fsm_decide(p.fsm, p.tab, p.tile_ss, p.tile_ss_l, p.tile_ss_r, nullptr, step + 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *p.ticket = 0u;
+    *p.fsm.pass_num = step;
+    if (p.sync && p.send_ack) {
+      // every CTA of this rank has finished reading its inboxes for `step`
+      fence_sys();
+      st_release_sys(p.ack_to_l, (uint32_t)step);
+      st_release_sys(p.ack_to_r, (uint32_t)step);
+    }
+  }
+}
+
+template <bool kMom>
+__global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const GossipParams p) {
+  const int b = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int step = *p.fsm.pass_num + 1;
+  const int n_tiles = p.tab.n_tiles;
+  const bool push = p.do_push != 0;
+
+  if (!(p.sync && push)) {
+    // ---------------- async (or no exchange): single pass, theta read once ----------------
+    for (int t = b; t < n_tiles; t += G) {
+      const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+      const F8 th = ld_f8(p.theta + base);
+      if (push && p.fsm.fire[p.tab.tile_tensor[t]]) push_tile(p, base, th);
+      mix_tile<kMom>(p, t, base, th, lane, warp);
+    }
+  } else {
+    // ---------------- iter-sync: software-pipelined push(q) | wait+mix(q-1) -----------------
+    __shared__ int s_ok;
+    if (tid == 0) {
+      // WAR guard: neighbours must have consumed what I pushed at step-1 before I overwrite it
+      bool ok = wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
+      ok = wait_ge(p.ack_from_r, (uint32_t)(step - 1), p.status, p.timeout_ns) && ok;
+      s_ok = ok;
+    }
+    __syncthreads();
+    const int Q = p.group_iters;
+    const int iters = (n_tiles + G - 1) / G;      // same on every CTA and every rank
+    const int n_groups = (iters + Q - 1) / Q;
+    for (int q = 0; q <= n_groups; ++q) {
+      if (q < n_groups) {
+        for (int j = q * Q; j < min(iters, (q + 1) * Q); ++j) {
+          const int t = b + j * G;
+          if (t < n_tiles && p.fsm.fire[p.tab.tile_tensor[t]]) {
+            const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+            push_tile(p, base, ld_f8(p.theta + base));
+          }
+        }
+        __syncthreads();   // all of this CTA's stores for group q are issued
+        if (tid == 0) {
+          fence_sys();     // ... and performed at system scope before the flags
+          st_release_sys(p.flag_to_l + (size_t)q * G + b, (uint32_t)step);
+          st_release_sys(p.flag_to_r + (size_t)q * G + b, (uint32_t)step);
+        }
+      }
+      if (q > 0) {
+        const int c = q - 1;
+        if (tid == 0) {
+          wait_ge(p.flag_from_l + (size_t)c * G + b, (uint32_t)step, p.status, p.timeout_ns);
+          wait_ge(p.flag_from_r + (size_t)c * G + b, (uint32_t)step, p.status, p.timeout_ns);
+        }
+        __syncthreads();
+        for (int j = c * Q; j < min(iters, (c + 1) * Q); ++j) {
+          const int t = b + j * G;
+          if (t < n_tiles) {
+            const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+            mix_tile<kMom>(p, t, base, ld_f8(p.theta + base), lane, warp);
+          }
+        }
+      }
+    }
+  }
+  grid_tail(p, step);
+}
+
+// (Re)compute tile partials (+ bf16 shadow) from theta; optionally evaluate the trigger for the
+// first step.  Used once at start-up and after theta is modified outside the step kernel
+// (checkpoint restore).
+__global__ void __launch_bounds__(EG_THREADS, 4) gossip_init_kernel(const GossipParams p, int run_fsm) {
+  const int b = blockIdx.x, G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = b; t < p.tab.n_tiles; t += G) {
+    const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+    const F8 th = ld_f8(p.theta + base);
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = __fmaf_rn(th.v[e], th.v[e], ss);
+    if (p.shadow != nullptr) st_bf16x8(p.shadow + base, th);
+    ss = warp_sum(ss);
+    if (lane == 0) p.tile_ss[(size_t)t * EG_WARPS + warp] = ss;
+  }
+  __shared__ int s_last;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(p.ticket, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (run_fsm) fsm_decide(p.fsm, p.tab, p.tile_ss, nullptr, nullptr, nullptr, *p.fsm.pass_num + 1);
+  __syncthreads();
+  if (tid == 0) *p.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(EG_THREADS) fsm_decide_kernel(const FsmDev f, const TableDev t,
+                                                               const float* ext_norm) {
+  fsm_decide(f, t, nullptr, nullptr, nullptr, ext_norm, *f.pass_num + 1);
+  __syncthreads();
+  if (threadIdx.x == 0) *f.pass_num += 1;
+}
+
+// -------------------------------------------------------------------------------------------
+int gossip_max_grid(int device) {
+  int sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int per_sm2 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gossip_step_kernel<true>, EG_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, gossip_step_kernel<false>, EG_THREADS, 0);
+  if (per_sm2 < per_sm) per_sm = per_sm2;
+  if (per_sm < 1) per_sm = 1;
+  return sms * per_sm;
+}
+
+cudaError_t launch_gossip_step(const GossipParams& p, int grid, cudaStream_t s) {
+  if (p.mu != 0.f && p.mom != nullptr)
+    gossip_step_kernel<true><<<grid, EG_THREADS, 0, s>>>(p);
+  else
+    gossip_step_kernel<false><<<grid, EG_THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gossip_init(const GossipParams& p, int grid, int run_fsm, cudaStream_t s) {
+  gossip_init_kernel<<<grid, EG_THREADS, 0, s>>>(p, run_fsm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fsm_decide(const FsmDev& f, const TableDev& t, const float* ext_norm, cudaStream_t s) {
+  fsm_decide_kernel<<<1, EG_THREADS, 0, s>>>(f, t, ext_norm);
+  return cudaGetLastError();
+}
+
+}  // namespace egb

@@ -57,7 +57,12 @@ class RingSimulator:
         return (r + 1) % self.R
 
     @torch.no_grad()
-    def step(self, grads: Sequence[torch.Tensor]) -> None:
+    def step(self, grads: Sequence[torch.Tensor], fires: Optional[Sequence[torch.Tensor]] = None,
+             norms: Optional[Sequence[torch.Tensor]] = None) -> None:
+        """`fires` (optional, one bool mask per rank) overrides the trigger decisions -- used to
+        compare the data path of a kernel bit-for-bit under the kernel's own decisions; `norms`
+        (optional, one [sz] tensor per rank) replaces the oracle's own norm computation so the FSM
+        logic can be compared exactly while norm accuracy is tested separately."""
         R, t = self.R, self.table
         self.pass_num += 1
         if self.algo == "cent":
@@ -72,8 +77,12 @@ class RingSimulator:
         # ---- phase 1: every rank decides and "Puts" (uses pre-mix theta_k) --------------
         if self.algo == "decent":
             fires = [torch.ones(t.n_tensors, dtype=torch.bool) for _ in range(R)]
+        elif fires is not None:
+            fires = [f.clone().bool().cpu() for f in fires]
         else:
-            fires = [trigger_step(self.state[r], self._norms(self.theta[r]), self.pass_num, self.tcfg)
+            fires = [trigger_step(self.state[r],
+                                  self._norms(self.theta[r]) if norms is None else norms[r].float().cpu(),
+                                  self.pass_num, self.tcfg)
                      for r in range(R)]
         self.fire_history.append([f.clone() for f in fires])
         snap = [th.clone() for th in self.theta]

@@ -22,7 +22,7 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
-TILE = 1024  # elements; must match EG_TILE in csrc/common.cuh
+TILE = 2048  # elements; must match EG_TILE in csrc/api.h
 
 
 @dataclass

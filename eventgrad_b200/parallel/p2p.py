@@ -1,0 +1,379 @@
+"""Fused peer-to-peer backend -- the product path.
+
+Per training step, after backward():
+  cent     ONE launch: one-/two-shot all-reduce over peer-mapped gradients fused with 1/R and SGD
+  decent   ONE launch: push theta to both ring neighbours -> flag handshake -> (t+L+R)/3 -> SGD
+  event    ONE launch: as decent, but a tensor is pushed only if its device-resident trigger fired;
+           the same kernel accumulates the norms and runs the trigger FSM for the next step
+  spevent  batched segmented radix-select top-k + compaction straight into the neighbours'
+           inboxes, scatter of arrived records into replicas, then the dense mix+SGD kernel
+No NCCL/MPI call, no separate elementwise kernel and no host synchronisation on that path
+(BASELINE.json north star).  Kernels: csrc/gossip.cu, csrc/allreduce.cu, csrc/sparse.cu.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from .arena import TILE, ParamArena, TensorTable
+from .base import CommBackend, StepLog
+from .window import DistBootstrap, Layout, Window
+
+ONE_SHOT_MAX_BYTES = 512 * 1024        # above this the all-reduce switches to two-shot
+DEFAULT_TIMEOUT_NS = 30_000_000_000    # a wedged peer trips the sticky status instead of hanging
+
+
+def _table_of(model) -> TensorTable:
+    return TensorTable.from_named(list(model.named_parameters()), TILE)
+
+
+def build_layout(table: TensorTable, cfg, world: int, max_grid: int) -> Layout:
+    lay = Layout()
+    n = table.n_padded * 4
+    lay.add("theta", n)
+    lay.add("grad", n)
+    if cfg.algo in ("decent", "event"):
+        lay.add("inbox_l", n)
+        lay.add("inbox_r", n)
+    if cfg.algo == "spevent":
+        K = sum(table.topk_counts(cfg.topk_percent))
+        lay.add("rec_from_l", 2 * K * 4)
+        lay.add("rec_from_r", 2 * K * 4)
+        lay.add("seq_from_l", table.n_tensors * 4)
+        lay.add("seq_from_r", table.n_tensors * 4)
+        lay.add("done_from_l", 256)
+        lay.add("done_from_r", 256)
+    nflag = (table.n_tiles + 2 * max_grid) * 4
+    lay.add("flag_from_l", nflag)
+    lay.add("flag_from_r", nflag)
+    lay.add("ack_from_l", 256)
+    lay.add("ack_from_r", 256)
+    lay.add("ar_flags", 3 * max_grid * world * 4)
+    return lay
+
+
+def preallocate_arena_buffers(model, cfg, env, group=None, bootstrap=None):
+    """Allocate this rank's window BEFORE the arena exists so that theta and grad live inside
+    peer-mapped memory (cent reads peers' gradients; final averaging reads peers' theta)."""
+    from ..ops import ext
+    C = ext()
+    table = _table_of(model)
+    max_grid = C.gossip_max_grid(env.device.index or 0)
+    lay = build_layout(table, cfg, env.world, max_grid)
+    win = Window(lay, env.rank, env.world, env.device)
+    theta = win.view("theta", torch.float32)
+    grad = win.view("grad", torch.float32)
+    return theta, grad, {"window": win, "max_grid": max_grid, "bootstrap": bootstrap}
+
+
+class P2PBackend(CommBackend):
+    name = "p2p"
+    zeroes_grad = True     # the fused kernels clear grad after consuming it
+
+    def __init__(self, cfg, arena: ParamArena, ring, env, group=None, symm=None,
+                 grid_cap: int = 0, defer_connect: bool = False, group_iters: int = 4,
+                 timeout_ns: int = DEFAULT_TIMEOUT_NS, vec256_push: bool = True):
+        super().__init__(cfg, arena, ring)
+        from ..ops import ext
+        self.C = ext()
+        if symm is None:
+            raise ValueError("P2PBackend needs the window that holds the arena (preallocate_arena_buffers)")
+        self.env, self.dev = env, arena.theta.device
+        self.win: Window = symm["window"]
+        self.boot = symm.get("bootstrap") or DistBootstrap(env, group)
+        self.table = arena.table
+        t = self.table
+        self.grid = min(t.n_tiles, symm["max_grid"])
+        if grid_cap:
+            self.grid = min(self.grid, grid_cap)
+        self.group_iters, self.timeout_ns, self.vec256_push = group_iters, timeout_ns, vec256_push
+        self.sync = cfg.sync_mode == "iter"
+        self.gossip = cfg.algo in ("decent", "event", "spevent")
+        self.sparse = cfg.algo == "spevent"
+        self.do_comm = self.comm_enabled and self.gossip
+        self.recv_rms = cfg.dataset == "mnist"
+        dev = self.dev
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=dev)
+        zf = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        zi = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        # ---- device tables ---------------------------------------------------------------
+        self.d_tile_tensor = t.tile_to_tensor().to(dev)
+        self.d_tile_start, self.d_tile_count, self.d_numel = i32(t.tile_start), i32(t.tile_count), i32(t.numels)
+        if self.sparse:
+            self.k = t.topk_counts(cfg.topk_percent)
+            msg = [2 * k * 4 for k in self.k]
+            rec_off, acc = [], 0
+            for k in self.k:
+                rec_off.append(acc)
+                acc += 2 * k
+            self.K = sum(self.k)
+            self.d_k, self.d_rec_off = i32(self.k), i32(rec_off)
+        else:
+            msg = [n * 4 for n in t.numels]
+        self.msg_bytes = msg
+        self.d_msg = i32(msg)
+        # ---- state -----------------------------------------------------------------------
+        H = max(1, cfg.sent_history)
+        self.thres, self.last_norm, self.last_iter = zf(t.n_tensors), zf(t.n_tensors), zf(t.n_tensors)
+        self.slopes = zf(t.n_tensors * H)
+        self.fire = torch.ones(t.n_tensors, dtype=torch.int32, device=dev)
+        self.cur_norm = zf(t.n_tensors)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.d_pass = zi(1)
+        self.ticket = zi(4)
+        self.status = zi(1)
+        self.tile_ss = zf(t.n_tiles * 8)
+        self.log_cap = 0
+        self.log_ring = None
+        self.tile_ss_l = self.tile_ss_r = None
+        if self.want_logs and cfg.algo in ("event", "spevent"):
+            self.log_cap = 4096
+            self.log_ring = zf(self.log_cap * t.n_tensors * 5)
+            self.tile_ss_l, self.tile_ss_r = zf(t.n_tiles * 8), zf(t.n_tiles * 8)
+            self._drained = 0
+            self._last_recv_l = torch.zeros(t.n_tensors)
+            self._last_recv_r = torch.zeros(t.n_tensors)
+        if self.sparse:
+            # Q8: prev / replicas start from theta_0 (identical on all ranks)
+            self.prev = arena.theta.clone()
+            self.rep_l = arena.theta.clone()
+            self.rep_r = arena.theta.clone()
+            self.hist = torch.zeros(t.n_tensors * 2048, dtype=torch.int32, device=dev)
+            self.sel_prefix, self.sel_remain = zi(t.n_tensors), zi(t.n_tensors)
+            self.tile_gt, self.tile_eq, self.t_gt_total = zi(t.n_tiles), zi(t.n_tiles), zi(t.n_tensors)
+            self.applied_l, self.applied_r = zi(t.n_tensors), zi(t.n_tensors)
+        self.ar_ctr = zi(1)
+        self.host_bytes = 0
+        self._connected = False
+        self.gp = self.ap = self.ap_avg = self.sp = None
+        if hasattr(self.boot, "publish"):
+            self.boot.publish("window_ptr", self.win.ptr)
+            self.boot.publish("grid", self.grid)
+        if not defer_connect:
+            self.connect()
+
+    # ------------------------------------------------------------------ wiring
+    def connect(self) -> None:
+        if self._connected:
+            return
+        boot, win, ring = self.boot, self.win, self.ring
+        if hasattr(boot, "collect"):
+            grids = boot.collect("grid")
+        else:
+            grids = boot.all_gather_object(self.grid)
+        self.grid = int(min(grids))          # identical persistent grid on every rank
+        boot.connect(win)
+        L, R = ring.left, ring.right
+        C, t, cfg = self.C, self.table, self.cfg
+        a = self.arena
+        P = lambda x: 0 if x is None else x.data_ptr()
+        tab = {"tab.tile_tensor": P(self.d_tile_tensor), "tab.t_tile_start": P(self.d_tile_start),
+               "tab.t_tile_count": P(self.d_tile_count), "tab.t_numel": P(self.d_numel),
+               "tab.t_msg_bytes": P(self.d_msg), "tab.n_tiles": t.n_tiles, "tab.n_tensors": t.n_tensors}
+        if self.gossip or True:
+            gp = C.GossipParams()
+            dense = cfg.algo in ("decent", "event")
+            gp.update(tab)
+            gp.update({
+                "theta": P(a.theta), "grad": P(a.grad), "mom": P(a.mom) if cfg.momentum != 0 else 0,
+                "tile_ss": P(self.tile_ss), "tile_ss_l": P(self.tile_ss_l), "tile_ss_r": P(self.tile_ss_r),
+                "ticket": P(self.ticket), "status": P(self.status), "timeout_ns": int(self.timeout_ns),
+                "lr": float(cfg.lr), "mu": float(cfg.momentum),
+                "do_mix": 1 if self.do_comm else 0,
+                "do_push": 1 if (self.do_comm and dense) else 0,
+                "sync": 1 if self.sync else 0,
+                "send_ack": 1 if dense else 0,
+                "zero_grad": 1, "group_iters": int(self.group_iters),
+                "vec256_push": 1 if self.vec256_push else 0,
+                "flag_from_l": win.addr("flag_from_l"), "flag_from_r": win.addr("flag_from_r"),
+                "flag_to_l": win.addr("flag_from_r", L), "flag_to_r": win.addr("flag_from_l", R),
+                "ack_from_l": win.addr("ack_from_l"), "ack_from_r": win.addr("ack_from_r"),
+                "ack_to_l": win.addr("ack_from_r", L), "ack_to_r": win.addr("ack_from_l", R),
+                "fsm.thres": P(self.thres), "fsm.last_norm": P(self.last_norm),
+                "fsm.last_iter": P(self.last_iter), "fsm.slopes": P(self.slopes),
+                "fsm.fire": P(self.fire), "fsm.cur_norm": P(self.cur_norm),
+                "fsm.counters": P(self.counters), "fsm.pass_num": P(self.d_pass),
+                "fsm.log_ring": P(self.log_ring), "fsm.log_cap": int(self.log_cap),
+                "fsm.horizon": float(cfg.horizon), "fsm.constant": float(cfg.constant),
+                "fsm.thres_type": int(cfg.thres_type), "fsm.history": max(1, int(cfg.sent_history)),
+                "fsm.initial_comm_passes": int(cfg.initial_comm_passes),
+                "fsm.enabled": 1 if (cfg.algo in ("event", "spevent") and self.do_comm) else 0,
+            })
+            if dense:
+                gp.update({"inbox_l": win.addr("inbox_l"), "inbox_r": win.addr("inbox_r"),
+                           "push_l": win.addr("inbox_r", L), "push_r": win.addr("inbox_l", R)})
+            elif self.sparse:
+                gp.update({"inbox_l": P(self.rep_l), "inbox_r": P(self.rep_r)})
+            self.gp = gp
+        if self.sparse:
+            sp = C.SparseParams()
+            sp.update(tab)
+            sp.update({
+                "theta": P(a.theta), "prev": P(self.prev), "rep_l": P(self.rep_l), "rep_r": P(self.rep_r),
+                "rec_from_l": win.addr("rec_from_l"), "rec_from_r": win.addr("rec_from_r"),
+                "rec_to_l": win.addr("rec_from_r", L), "rec_to_r": win.addr("rec_from_l", R),
+                "seq_from_l": win.addr("seq_from_l"), "seq_from_r": win.addr("seq_from_r"),
+                "seq_to_l": win.addr("seq_from_r", L), "seq_to_r": win.addr("seq_from_l", R),
+                "applied_l": P(self.applied_l), "applied_r": P(self.applied_r),
+                "done_from_l": win.addr("done_from_l"), "done_from_r": win.addr("done_from_r"),
+                "done_to_l": win.addr("done_from_r", L), "done_to_r": win.addr("done_from_l", R),
+                "ack_from_l": win.addr("ack_from_l"), "ack_from_r": win.addr("ack_from_r"),
+                "ack_to_l": win.addr("ack_from_r", L), "ack_to_r": win.addr("ack_from_l", R),
+                "t_k": P(self.d_k), "t_rec_off": P(self.d_rec_off), "hist": P(self.hist),
+                "sel_prefix": P(self.sel_prefix), "sel_remain": P(self.sel_remain),
+                "tile_gt": P(self.tile_gt), "tile_eq": P(self.tile_eq), "t_gt_total": P(self.t_gt_total),
+                "fire": P(self.fire), "pass_num": P(self.d_pass), "ticket": P(self.ticket[1:]),
+                "status": P(self.status), "timeout_ns": int(self.timeout_ns), "sync": 1 if self.sync else 0,
+            })
+            self.sp = sp
+        # ---- all-reduce parameter blocks (cent step; final averaging for every algorithm) ----
+        W = self.ring.world
+        self.d_peer_grad = torch.tensor([win.addr("grad", r) for r in range(W)], dtype=torch.int64, device=self.dev)
+        self.d_peer_theta = torch.tensor([win.addr("theta", r) for r in range(W)], dtype=torch.int64, device=self.dev)
+        self.d_peer_flags = torch.tensor([win.addr("ar_flags", r) for r in range(W)], dtype=torch.int64, device=self.dev)
+        common = {"peer_flags": P(self.d_peer_flags), "flags": win.addr("ar_flags"),
+                  "ticket": P(self.ticket[2:]), "status": P(self.status), "step_ctr": P(self.ar_ctr),
+                  "timeout_ns": int(self.timeout_ns), "n_tiles": t.n_tiles, "rank": self.ring.rank,
+                  "world": W, "lr": float(cfg.lr), "mu": float(cfg.momentum)}
+        ap = C.AllReduceParams()
+        ap.update(common)
+        ap.update({"peer_bufs": P(self.d_peer_grad), "local": P(a.grad), "theta": P(a.theta),
+                   "mom": P(a.mom) if cfg.momentum != 0 else 0, "mode": 1, "zero_after": 1,
+                   "two_shot": 1 if t.n_padded * 4 > ONE_SHOT_MAX_BYTES else 0})
+        self.ap = ap
+        av = C.AllReduceParams()
+        av.update(common)
+        av.update({"peer_bufs": P(self.d_peer_theta), "local": P(a.theta), "mode": 0, "zero_after": 0,
+                   "two_shot": 1})
+        self.ap_avg = av
+        self._connected = True
+        if self.gossip:
+            self._init_norms(run_fsm=True)
+        boot.barrier()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _init_norms(self, run_fsm: bool) -> None:
+        with torch.cuda.device(self.dev):
+            self.C.gossip_init(self.gp, self.grid, 1 if run_fsm else 0, self._stream())
+
+    # ------------------------------------------------------------------ step
+    def step(self) -> None:
+        self.pass_num += 1
+        C, s = self.C, self._stream()
+        with torch.cuda.device(self.dev):
+            if self.cfg.algo == "cent":
+                if self.ring.world > 1:
+                    C.allreduce(self.ap, self.grid, s)
+                    self.host_bytes += self.table.n_elems * 4
+                else:
+                    C.gossip_step(self.gp, self.grid, s)       # plain fused SGD
+                return
+            if self.sparse and self.do_comm:
+                C.sparse_select_push(self.sp, self.grid, s)
+                C.sparse_apply(self.sp, self.grid, s)
+            C.gossip_step(self.gp, self.grid, s)
+        if self.cfg.algo == "decent" and self.do_comm:
+            self.host_bytes += 2 * self.table.n_elems * 4
+
+    # ------------------------------------------------------------------ end of training
+    def check_status(self) -> None:
+        st = int(self.status.item())
+        if st != 0:
+            raise RuntimeError(f"p2p backend: device status {st} (1 = peer wait timed out) on rank {self.ring.rank}")
+
+    def final_average_nocheck(self) -> None:
+        if self.ring.world == 1:
+            return
+        with torch.cuda.device(self.dev):
+            self.C.allreduce(self.ap_avg, self.grid, self._stream())
+        if not self.cfg.final_divide_all and self.ring.rank != 0:
+            self.arena.theta.mul_(float(self.ring.world))     # reference quirk Q5: only rank 0 divides
+
+    def final_average(self) -> None:
+        self.final_average_nocheck()
+        self.check_status()
+
+    def num_events(self) -> int:
+        return int(self.counters[0].item())
+
+    def total_events(self) -> int:
+        ev = self.num_events()
+        if self.ring.world == 1 or not hasattr(self.boot, "all_gather_object"):
+            return ev
+        return int(sum(self.boot.all_gather_object(ev)))
+
+    def bytes_sent(self) -> int:
+        return int(self.counters[1].item()) + self.host_bytes
+
+    def synchronize(self) -> None:
+        torch.cuda.synchronize(self.dev)
+
+    # ------------------------------------------------------------------ logs
+    def drain_logs(self) -> List[StepLog]:
+        if self.log_ring is None:
+            return []
+        torch.cuda.synchronize(self.dev)
+        t = self.table
+        ring = self.log_ring.view(self.log_cap, t.n_tensors, 5).cpu()
+        out = []
+        numel = torch.tensor(t.numels, dtype=torch.float32)
+        for s in range(self._drained + 1, self.pass_num + 1):
+            row = ring[(s - 1) % self.log_cap]
+            ln, rn = row[:, 3].clone(), row[:, 4].clone()
+            if self.recv_rms:
+                ln, rn = ln / numel.sqrt(), rn / numel.sqrt()
+            lnew = (ln - self._last_recv_l).abs() > 0
+            rnew = (rn - self._last_recv_r).abs() > 0
+            self._last_recv_l = torch.where(lnew, ln, self._last_recv_l)
+            self._last_recv_r = torch.where(rnew, rn, self._last_recv_r)
+            out.append(StepLog(s, row[:, 0].clone(), row[:, 1].clone(), row[:, 2] > 0.5, ln, rn, lnew, rnew))
+        self._drained = self.pass_num
+        return out
+
+    # ------------------------------------------------------------------ checkpoint
+    def state_dict(self):
+        torch.cuda.synchronize(self.dev)
+        sd = {"pass_num": self.pass_num, "host_bytes": self.host_bytes}
+        for k in ("thres", "last_norm", "last_iter", "slopes", "fire", "cur_norm", "counters", "d_pass"):
+            sd[k] = getattr(self, k).cpu().clone()
+        if self.cfg.algo in ("decent", "event"):
+            sd["inbox_l"] = self.win.view("inbox_l", torch.float32).cpu().clone()
+            sd["inbox_r"] = self.win.view("inbox_r", torch.float32).cpu().clone()
+        if self.sparse:
+            for k in ("prev", "rep_l", "rep_r"):
+                sd[k] = getattr(self, k).cpu().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        self.pass_num = int(sd["pass_num"])
+        self.host_bytes = int(sd.get("host_bytes", 0))
+        for k in ("thres", "last_norm", "last_iter", "slopes", "fire", "cur_norm", "counters", "d_pass"):
+            getattr(self, k).copy_(sd[k].to(self.dev))
+        if "inbox_l" in sd and self.cfg.algo in ("decent", "event"):
+            self.win.view("inbox_l", torch.float32).copy_(sd["inbox_l"].to(self.dev))
+            self.win.view("inbox_r", torch.float32).copy_(sd["inbox_r"].to(self.dev))
+        if self.sparse:
+            for k in ("prev", "rep_l", "rep_r"):
+                getattr(self, k).copy_(sd[k].to(self.dev))
+        # NOTE: handshake counters (flags / acks) restart from pass_num on every rank
+        if self.gossip:
+            self._init_norms(run_fsm=False)
+            self._reset_handshake(self.pass_num)
+        torch.cuda.synchronize(self.dev)
+
+    def _reset_handshake(self, step: int) -> None:
+        for name in ("flag_from_l", "flag_from_r", "ack_from_l", "ack_from_r"):
+            self.win.view(name, torch.int32).fill_(step)
+        if self.sparse:
+            for name in ("done_from_l", "done_from_r"):
+                self.win.view(name, torch.int32).fill_(step)
+
+    def close(self) -> None:
+        try:
+            torch.cuda.synchronize(self.dev)
+        except Exception:
+            pass
+        self.win.close()

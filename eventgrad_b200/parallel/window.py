@@ -1,0 +1,168 @@
+"""Peer-mapped memory windows -- the B200-native replacement of the reference's MPI RMA window
+(MPI_Alloc_mem + MPI_Win_create, /root/reference/dmnist/event/event.cpp:170-179).
+
+Every rank owns one device slab with an identical layout on all ranks (so "the same offset in
+my neighbour's slab" is the reference's `target_disp`).  Slabs are exported with CUDA IPC
+(native runtime: csrc/ipc.cu), the 64-byte handles are exchanged once through the process
+group, and each rank maps its peers' slabs.  A kernel-side `st.global` to a mapped address is
+the `MPI_Put`: it crosses NVLink 5 / NVSwitch directly into the peer's HBM.
+
+Two bootstraps implement the same interface:
+  DistBootstrap   one process per GPU (torchrun); handles travel via all_gather_object
+  LocalBootstrap  R virtual ranks inside ONE process on ONE GPU (peer pointer == the other
+                  virtual rank's local pointer).  Used by the single-GPU tests to exercise the
+                  complete cross-rank protocol (flags, acks, pushes) without torchrun.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+_DT = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.int64: "<i8",
+       torch.bfloat16: None}
+
+
+class _RawCuda:
+    """Minimal __cuda_array_interface__ holder so torch can alias raw device memory."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
+                                         "data": (ptr, False), "version": 2}
+
+
+def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    """uint8 tensor aliasing [ptr, ptr+nbytes) on `device` (no copy, no ownership)."""
+    t = torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+    assert t.data_ptr() == ptr, "as_tensor copied instead of aliasing"
+    return t
+
+
+class Layout:
+    """Named, 256-byte aligned sections inside a slab."""
+
+    def __init__(self):
+        self.sections: Dict[str, Tuple[int, int]] = {}
+        self.size = 0
+
+    def add(self, name: str, nbytes: int) -> None:
+        off = (self.size + 255) // 256 * 256
+        self.sections[name] = (off, nbytes)
+        self.size = off + nbytes
+
+    def offset(self, name: str) -> int:
+        return self.sections[name][0]
+
+    def nbytes(self, name: str) -> int:
+        return self.sections[name][1]
+
+
+class Window:
+    """One rank's slab + the mapped views of its peers."""
+
+    def __init__(self, layout: Layout, rank: int, world: int, device: torch.device):
+        from ..ops import ext
+        self._C = ext()
+        self.layout, self.rank, self.world, self.device = layout, rank, world, device
+        with torch.cuda.device(device):
+            self.ptr, self.handle = self._C.ipc_alloc(max(256, layout.size))
+        self.raw = tensor_from_ptr(self.ptr, max(256, layout.size), device)
+        self.peer_ptrs: List[int] = [0] * world
+        self.peer_ptrs[rank] = self.ptr
+        self._opened: List[int] = []
+        self._closed = False
+
+    # ---- local views ------------------------------------------------------------------
+    def view(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        off, nb = self.layout.sections[name]
+        return self.raw[off: off + nb].view(dtype)
+
+    def addr(self, name: str, rank: Optional[int] = None) -> int:
+        base = self.ptr if rank is None else self.peer_ptrs[rank]
+        if base == 0:
+            raise RuntimeError(f"peer {rank} not mapped")
+        return base + self.layout.offset(name)
+
+    # ---- mapping ----------------------------------------------------------------------
+    def connect_handles(self, handles: List[bytes]) -> None:
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = self._C.ipc_open(h)
+                self.peer_ptrs[r] = p
+                self._opened.append(p)
+
+    def connect_local(self, ptrs: List[int]) -> None:
+        for r, p in enumerate(ptrs):
+            self.peer_ptrs[r] = p
+
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.device(self.device):
+                for p in self._opened:
+                    self._C.ipc_close(p)
+                self.raw = None
+                self._C.ipc_free(self.ptr)
+        except Exception:
+            pass
+
+
+class DistBootstrap:
+    def __init__(self, env, group=None):
+        self.rank, self.world, self.group = env.rank, env.world, group
+
+    def all_gather_object(self, obj):
+        if self.world == 1:
+            return [obj]
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def connect(self, win: Window) -> None:
+        handles = self.all_gather_object(win.handle)
+        win.connect_handles(handles)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
+
+class LocalBootstrap:
+    """Rendezvous board shared by R virtual ranks living in the same process."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.board: Dict[str, Dict[int, object]] = {}
+
+    def for_rank(self, rank: int) -> "_LocalRankView":
+        return _LocalRankView(self, rank)
+
+
+class _LocalRankView:
+    def __init__(self, parent: LocalBootstrap, rank: int):
+        self.parent, self.rank, self.world = parent, rank, parent.world
+
+    def publish(self, key: str, obj) -> None:
+        self.parent.board.setdefault(key, {})[self.rank] = obj
+
+    def collect(self, key: str):
+        b = self.parent.board.get(key, {})
+        if len(b) != self.world:
+            raise RuntimeError(f"local rendezvous '{key}': {len(b)}/{self.world} ranks published")
+        return [b[r] for r in range(self.world)]
+
+    def connect(self, win: Window) -> None:
+        win.connect_local(self.collect("window_ptr"))
+
+    def barrier(self) -> None:
+        pass

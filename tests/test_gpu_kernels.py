@@ -1,0 +1,265 @@
+"""GPU numerics: every fused kernel against a plain PyTorch fp32 reference of the same op.
+
+Multi-rank behaviour is exercised on ONE GPU through ops.local_world.LocalWorld: R virtual
+ranks (own window / arena / stream each) whose kernels really handshake through flags in
+device memory.  Golden model: engine.simulator.RingSimulator.
+"""
+import math
+
+import pytest
+import torch
+
+from eventgrad_b200.config import TrainConfig
+from eventgrad_b200.engine.simulator import RingSimulator
+from eventgrad_b200.models import build_model
+from eventgrad_b200.parallel.trigger import TriggerConfig, TriggerState, trigger_step
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(algo, **kw):
+    base = dict(algo=algo, dataset="mnist", model="cnn2", lr=0.05, momentum=0.9, sync_mode="iter",
+                horizon=1.0, thres_type=1, topk_percent=10.0)
+    base.update(kw)
+    return TrainConfig(**base).validate()
+
+
+def _world(cfg, R, model="cnn2", **kw):
+    from eventgrad_b200.ops.local_world import LocalWorld
+    return LocalWorld(cfg, R, lambda: build_model(model), grid_cap=kw.pop("grid_cap", 6),
+                      timeout_ns=5_000_000_000, **kw)
+
+
+def _grads(world, n, seed, scale=0.05):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    out = []
+    for r in range(world):
+        x = torch.randn(n, generator=g, device="cuda") * scale
+        out.append(x)
+    return out
+
+
+def _mask_pad(w, g):
+    """zero the padding lanes of a flat gradient (real grads never touch them)."""
+    t = w.arenas[0].table
+    m = torch.zeros(t.n_padded, device="cuda")
+    for o, n in zip(t.offsets, t.numels):
+        m[o:o + n] = 1
+    return [x * m for x in g]
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4])
+@pytest.mark.parametrize("mu", [0.0, 0.9])
+def test_decent_bitwise_vs_simulator(R, mu):
+    cfg = _cfg("decent", momentum=mu)
+    w = _world(cfg, R)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "decent", lr=cfg.lr, momentum=mu, serial_skip=False)
+    for s in range(5):
+        g = _mask_pad(w, _grads(R, t.n_padded, 100 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g])
+    torch.cuda.synchronize()
+    for be in w.backends:
+        be.check_status()
+    for r in range(R):
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r} theta differs"
+        assert float(w.arenas[r].grad.abs().max()) == 0.0        # fused zero_grad
+    w.close()
+
+
+@pytest.mark.parametrize("R", [2, 4])
+@pytest.mark.parametrize("thres", [(1, 1.0), (1, 0.9), (0, 0.0), (0, 1e9)])
+def test_event_vs_simulator(R, thres):
+    tt, val = thres
+    cfg = _cfg("event", thres_type=tt, horizon=val, constant=val, initial_comm_passes=5)
+    w = _world(cfg, R)
+    t = w.arenas[0].table
+    tc = TriggerConfig.from_train(cfg)
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "event", tc, lr=cfg.lr, momentum=cfg.momentum)
+    steps = 25
+    for s in range(steps):
+        fires = [be.fire.clone().bool() for be in w.backends]      # decisions the kernel will act on
+        g = _mask_pad(w, _grads(R, t.n_padded, 7 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g], fires=fires)
+    torch.cuda.synchronize()
+    for r, be in enumerate(w.backends):
+        be.check_status()
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r}"
+        assert be.num_events() == sim.events[r]
+        assert be.bytes_sent() == sim.bytes[r]
+    if tt == 0 and val == 0.0:
+        assert sum(sim.events) == 2 * t.n_tensors * steps * R      # threshold 0 == dense D-PSGD
+    if tt == 0 and val == 1e9:
+        assert sum(sim.events) == 2 * t.n_tensors * 4 * R          # only the forced warm-up sends
+    w.close()
+
+
+def test_event_decisions_match_oracle():
+    """Free-running kernel FSM (norm-on-write + device trigger) vs the PyTorch oracle FSM."""
+    R = 2
+    cfg = _cfg("event", horizon=0.95, initial_comm_passes=5)
+    w = _world(cfg, R)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "event", TriggerConfig.from_train(cfg), lr=cfg.lr,
+                        momentum=cfg.momentum)
+    mism = tot = 0
+    for s in range(30):
+        fires = [be.fire.clone().bool().cpu() for be in w.backends]
+        knorms = [be.cur_norm.clone() for be in w.backends]          # norm-on-write results
+        for r in range(R):                                            # ... which must be accurate
+            torch.testing.assert_close(knorms[r].cpu(), sim._norms(sim.theta[r]), rtol=3e-6, atol=1e-7)
+        g = _mask_pad(w, _grads(R, t.n_padded, 500 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g], norms=knorms)
+        for r in range(R):
+            mism += int((fires[r] != sim.fire_history[-1][r]).sum())
+            tot += t.n_tensors
+        if mism:
+            break      # trajectories diverge after the first differing decision
+    torch.cuda.synchronize()
+    assert mism == 0, f"{mism}/{tot} trigger decisions differ from the oracle"
+    for r in range(R):
+        torch.testing.assert_close(w.arenas[r].theta.cpu(), sim.theta[r], rtol=0, atol=0)
+    w.close()
+
+
+def test_fsm_kernel_vs_oracle_random_norms():
+    from eventgrad_b200.ops.local_world import LocalWorld
+    cfg = _cfg("event", horizon=0.9, initial_comm_passes=3)
+    w = _world(cfg, 1)
+    be = w.backends[0]
+    sz = w.arenas[0].table.n_tensors
+    tc = TriggerConfig.from_train(cfg)
+    st = TriggerState(sz, cfg.sent_history)
+    # reset device FSM to a clean state
+    for x in (be.thres, be.last_norm, be.last_iter, be.slopes):
+        x.zero_()
+    be.d_pass.zero_()
+    g = torch.Generator().manual_seed(0)
+    norms = torch.rand(sz, generator=g) + 1.0
+    for k in range(1, 40):
+        norms = norms + (torch.rand(sz, generator=g) - 0.45) * 0.01 * (1 + (k % 7 == 0) * 5)
+        dn = norms.float().cuda()
+        be.C.fsm_decide(be.gp, dn.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        fire = trigger_step(st, norms.float(), k, tc)
+        assert torch.equal(be.fire.cpu().bool(), fire), f"step {k}"
+        assert torch.equal(be.thres.cpu(), st.thres)
+        assert torch.equal(be.last_norm.cpu(), st.last_norm)
+        assert torch.equal(be.slopes.cpu().view(sz, -1), st.slopes)
+    w.close()
+
+
+@pytest.mark.parametrize("R", [2, 3])
+@pytest.mark.parametrize("pct", [1.0, 10.0, 100.0])
+def test_spevent_vs_simulator(R, pct):
+    cfg = _cfg("spevent", topk_percent=pct, initial_comm_passes=4, horizon=1.0)
+    w = _world(cfg, R)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "spevent", TriggerConfig.from_train(cfg), lr=cfg.lr,
+                        momentum=cfg.momentum, topk_percent=pct)
+    for s in range(12):
+        fires = [be.fire.clone().bool() for be in w.backends]
+        g = _mask_pad(w, _grads(R, t.n_padded, 900 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g], fires=fires)
+    torch.cuda.synchronize()
+    for r, be in enumerate(w.backends):
+        be.check_status()
+        assert torch.equal(be.prev.cpu(), sim.prev[r]), f"prev rank {r}"
+        assert torch.equal(be.rep_l.cpu(), sim.rep_l[r]), f"rep_l rank {r}"
+        assert torch.equal(be.rep_r.cpu(), sim.rep_r[r]), f"rep_r rank {r}"
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"theta rank {r}"
+        assert be.num_events() == sim.events[r]
+        assert be.bytes_sent() == sim.bytes[r]
+    w.close()
+
+
+@pytest.mark.parametrize("R", [2, 4])
+@pytest.mark.parametrize("model", ["mlp", "resnet18"])
+def test_cent_allreduce_vs_reference(R, model):
+    cfg = _cfg("cent", model=model, momentum=0.0 if model == "mlp" else 0.9, lr=1e-2)
+    w = _world(cfg, R, model=model, grid_cap=16)
+    t = w.arenas[0].table
+    theta0 = w.arenas[0].theta.clone()
+    mom = torch.zeros_like(theta0)
+    ref = theta0.clone()
+    for s in range(3):
+        g = _mask_pad(w, _grads(R, t.n_padded, 40 + s))
+        w.step(g)
+        acc = g[0].clone()
+        for r in range(1, R):
+            acc = acc + g[r]                       # rank order, fp32
+        gbar = acc / float(R)
+        if cfg.momentum:
+            mom = mom * cfg.momentum + gbar
+            ref = torch.addcmul(ref, mom, torch.tensor(-cfg.lr, device="cuda"))
+        else:
+            ref = torch.addcmul(ref, gbar, torch.tensor(-cfg.lr, device="cuda"))
+    torch.cuda.synchronize()
+    for r, be in enumerate(w.backends):
+        be.check_status()
+        torch.testing.assert_close(w.arenas[r].theta, ref, rtol=1e-6, atol=1e-7)
+        assert torch.equal(w.arenas[r].theta, w.arenas[0].theta)       # replicas stay bit-identical
+        assert float(w.arenas[r].grad.abs().max()) == 0.0
+    w.close()
+
+
+def test_final_average():
+    R = 3
+    cfg = _cfg("event")
+    w = _world(cfg, R)
+    n = w.arenas[0].table.n_padded
+    vals = [torch.randn(n, device="cuda") for _ in range(R)]
+    for r in range(R):
+        w.arenas[r].theta.copy_(vals[r])
+    torch.cuda.synchronize()
+    w.final_average()
+    ref = ((vals[0] + vals[1]) + vals[2]) / 3.0
+    for r in range(R):
+        torch.testing.assert_close(w.arenas[r].theta, ref, rtol=1e-6, atol=1e-7)
+        assert torch.equal(w.arenas[r].theta, w.arenas[0].theta)
+    w.close()
+
+
+def test_async_mode_runs_and_counts():
+    R = 2
+    cfg = _cfg("event", sync_mode="async", thres_type=0, constant=0.0)
+    w = _world(cfg, R)
+    t = w.arenas[0].table
+    for s in range(6):
+        w.step(_mask_pad(w, _grads(R, t.n_padded, s)))
+    torch.cuda.synchronize()
+    for be in w.backends:
+        be.check_status()
+        assert be.num_events() == 2 * t.n_tensors * 6
+    assert all(torch.isfinite(a.theta).all() for a in w.arenas)
+    w.close()
+
+
+def test_norm_on_write_matches_torch_norm():
+    cfg = _cfg("event", model="resnet18", dataset="cifar10")
+    w = _world(cfg, 1, model="resnet18", grid_cap=64)
+    a, be = w.arenas[0], w.backends[0]
+    ref = a.tensor_norms()
+    torch.testing.assert_close(be.cur_norm, ref, rtol=2e-6, atol=1e-7)
+    w.close()
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_decode_augment_kernel(nhwc, bf16):
+    from eventgrad_b200.data.augment import decode_augment_torch, draw_augment_params
+    from eventgrad_b200.ops.augment import decode_augment
+    x = torch.randint(0, 256, (37, 3, 32, 32), dtype=torch.uint8, device="cuda")
+    p = draw_augment_params(37, 4, "cuda")
+    dt = torch.bfloat16 if bf16 else torch.float32
+    out = decode_augment(x, 1 / 255.0, 0.45, 0.25, p, out_dtype=dt, channels_last=nhwc)
+    ref = decode_augment_torch(x, 1 / 255.0, 0.45, 0.25, p, out_dtype=dt)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1e-2 if bf16 else 1e-6, atol=1e-2 if bf16 else 1e-6)
+    if nhwc:
+        assert out.is_contiguous(memory_format=torch.channels_last)
+    out2 = decode_augment(x, 1.0, 0.0, 1.0, None)
+    assert torch.equal(out2, x.float())
