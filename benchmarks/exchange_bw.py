@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the fused exchange kernels on N GPUs (torchrun), device-timed, max over ranks.
+
+For the ResNet arena (69.8 MB of parameters, 86 tensors) it reports per launch:
+  * fused dense gossip step (push both neighbours + handshake + mix + SGD + norm-on-write):
+    time, NVLink egress GB/s per GPU (2 x model bytes / time) against the measured 770 GB/s
+    per-direction peer-copy ceiling, and HBM bytes/s of the mix+SGD stream;
+  * fused event step at a chosen fire fraction (bytes scale with events);
+  * fused all-reduce(+1/R+SGD) vs NCCL all_reduce + eager scale + eager SGD;
+  * the NCCL-only gossip baseline (batch_isend_irecv + eager mix + eager SGD).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from eventgrad_b200.config import TrainConfig  # noqa: E402
+from eventgrad_b200.models import build_model  # noqa: E402
+from eventgrad_b200.parallel import ParamArena, Ring  # noqa: E402
+from eventgrad_b200.parallel.collective import CollectiveBackend  # noqa: E402
+from eventgrad_b200.parallel.p2p import P2PBackend, preallocate_arena_buffers  # noqa: E402
+from eventgrad_b200.utils.dist import barrier, init_distributed, max_over_ranks, shutdown  # noqa: E402
+
+
+def timed(fn, env, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    barrier(env)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(env)
+    return max_over_ranks(e0.elapsed_time(e1), env) / iters
+
+
+def make(cfg, env, model_name, **kw):
+    torch.manual_seed(0)
+    model = build_model(model_name)
+    theta, grad, symm = preallocate_arena_buffers(model, cfg, env)
+    arena = ParamArena(model, env.device, theta=theta, grad=grad)
+    be = P2PBackend(cfg, arena, Ring(env.rank, env.world), env, symm=symm, **kw)
+    return arena, be
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="resnet18")
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--skip-nccl", action="store_true")
+    a = ap.parse_args()
+    env = init_distributed("cuda")
+    W = env.world
+    res = {"world": W, "model": a.model}
+    base = dict(dataset="mnist", model=a.model, lr=1e-2, momentum=0.9)   # mnist => comm even at W=1 (self loop)
+
+    # ---- dense fused gossip (decent) -----------------------------------------------------------
+    for name, kw in (("v256", dict(vec256_push=True)), ("v128", dict(vec256_push=False)),
+                     ("q1", dict(group_iters=1)), ("q16", dict(group_iters=16))):
+        cfg = TrainConfig(algo="decent", sync_mode="iter", **base).validate()
+        arena, be = make(cfg, env, a.model, **kw)
+        n_bytes = arena.table.n_elems * 4
+        ms = timed(be.step, env, a.iters)
+        be.check_status()
+        res[f"gossip_dense_{name}"] = {"ms": ms, "egress_GBps_per_gpu": 2 * n_bytes / ms / 1e6,
+                                      "frac_of_770": 2 * n_bytes / ms / 1e6 / 770,
+                                      "hbm_GBps": 9 * arena.table.n_padded * 4 / ms / 1e6, "grid": be.grid}
+        be.close()
+        del arena, be
+        torch.cuda.empty_cache()
+
+    # ---- async dense (no handshake) and event at ~0 fire fraction -------------------------------
+    cfg = TrainConfig(algo="event", sync_mode="async", thres_type=0, constant=0.0, **base).validate()
+    arena, be = make(cfg, env, a.model)
+    n_bytes = arena.table.n_elems * 4
+    ms = timed(be.step, env, a.iters)
+    res["event_async_allfire"] = {"ms": ms, "egress_GBps_per_gpu": 2 * n_bytes / ms / 1e6}
+    be.close(); del arena, be; torch.cuda.empty_cache()
+    cfg = TrainConfig(algo="event", sync_mode="iter", thres_type=0, constant=1e30, initial_comm_passes=0,
+                      **base).validate()
+    arena, be = make(cfg, env, a.model)
+    ms = timed(be.step, env, a.iters)
+    res["event_sync_nofire"] = {"ms": ms, "hbm_GBps": 7 * arena.table.n_padded * 4 / ms / 1e6,
+                                "events": be.num_events()}
+    be.close(); del arena, be; torch.cuda.empty_cache()
+
+    # ---- sparse 1% / 10% -----------------------------------------------------------------------
+    for pct in (1.0, 10.0):
+        cfg = TrainConfig(algo="spevent", sync_mode="iter", thres_type=0, constant=0.0, topk_percent=pct,
+                          **base).validate()
+        arena, be = make(cfg, env, a.model)
+        def stp():
+            arena.grad.normal_(0, 0.01)
+            be.step()
+        ms = timed(stp, env, max(10, a.iters // 3))
+        ms_g = timed(lambda: arena.grad.normal_(0, 0.01), env, 20)
+        res[f"spevent_{pct:g}pct"] = {"ms": ms - ms_g, "K": be.K}
+        be.check_status()
+        be.close(); del arena, be; torch.cuda.empty_cache()
+
+    # ---- fused all-reduce + SGD (cent) vs NCCL ------------------------------------------------
+    for model in ("mlp", a.model):
+        cfg = TrainConfig(algo="cent", **dict(base, model=model)).validate()
+        arena, be = make(cfg, env, model)
+        n_bytes = arena.table.n_elems * 4
+        ms = timed(be.step, env, a.iters)
+        be.check_status()
+        entry = {"ms_fused": ms, "bytes": n_bytes,
+                 "busbw_GBps": (2 * (W - 1) / W) * n_bytes / ms / 1e6 if W > 1 else 0.0}
+        if W > 1 and not a.skip_nccl:
+            g = torch.zeros(arena.table.n_padded, device=env.device)
+            th, mom = torch.zeros_like(g), torch.zeros_like(g)
+            def nccl_step():
+                dist.all_reduce(g)
+                g.div_(W)
+                mom.mul_(0.9).add_(g)
+                th.add_(mom, alpha=-1e-2)
+                g.zero_()
+            entry["ms_nccl_eager"] = timed(nccl_step, env, a.iters)
+        res[f"allreduce_sgd_{model}"] = entry
+        be.close(); del arena, be; torch.cuda.empty_cache()
+
+    # ---- NCCL-only gossip baseline -------------------------------------------------------------
+    if W > 1 and not a.skip_nccl:
+        cfg = TrainConfig(algo="decent", backend="nccl", **base).validate()
+        torch.manual_seed(0)
+        model = build_model(a.model)
+        arena = ParamArena(model, env.device)
+        be = CollectiveBackend(cfg, arena, Ring(env.rank, W))
+        def st():
+            arena.grad.zero_()
+            be.step()
+        res["gossip_dense_nccl_baseline"] = {"ms": timed(st, env, max(10, a.iters // 2))}
+
+    if env.rank == 0:
+        print(json.dumps(res, indent=1))
+        if a.out:
+            os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+            json.dump(res, open(a.out, "w"), indent=1)
+    shutdown()
+
+
+if __name__ == "__main__":
+    main()
