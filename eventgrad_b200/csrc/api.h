@@ -70,6 +70,7 @@ struct GossipParams {
   uint32_t* ack_to_l;       // peer-mapped
   uint32_t* ack_to_r;
   unsigned int* ticket;     // last-CTA election
+  unsigned int* tensor_done; // [sz] per-tensor count of per-warp partials written this launch
   int* status;              // sticky error word
   unsigned long long timeout_ns;
   TableDev tab;
@@ -83,6 +84,7 @@ struct GossipParams {
   int zero_grad;
   int group_iters;          // tiles per CTA between two flag publications (sync)
   int vec256_push;          // 1: 256-bit peer stores, 0: 2x128-bit
+  int need_norm;            // 0: skip norm-on-write + trigger entirely (decent/cent without logs)
 };
 
 int gossip_max_grid(int device);  // co-resident CTAs (persistent grid upper bound)

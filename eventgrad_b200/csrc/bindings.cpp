@@ -42,11 +42,11 @@ static const std::unordered_map<std::string, Setter<GossipParams>> kGossip = {
     PTRF(GossipParams, tile_ss_l), PTRF(GossipParams, tile_ss_r), PTRF(GossipParams, flag_from_l),
     PTRF(GossipParams, flag_from_r), PTRF(GossipParams, flag_to_l), PTRF(GossipParams, flag_to_r),
     PTRF(GossipParams, ack_from_l), PTRF(GossipParams, ack_from_r), PTRF(GossipParams, ack_to_l),
-    PTRF(GossipParams, ack_to_r), PTRF(GossipParams, ticket), PTRF(GossipParams, status),
+    PTRF(GossipParams, ack_to_r), PTRF(GossipParams, ticket), PTRF(GossipParams, tensor_done), PTRF(GossipParams, status),
     NUMF(GossipParams, timeout_ns), NUMF(GossipParams, lr), NUMF(GossipParams, mu),
     NUMF(GossipParams, do_mix), NUMF(GossipParams, do_push), NUMF(GossipParams, sync),
     NUMF(GossipParams, send_ack), NUMF(GossipParams, zero_grad), NUMF(GossipParams, group_iters),
-    NUMF(GossipParams, vec256_push), TAB_FIELDS(GossipParams),
+    NUMF(GossipParams, vec256_push), NUMF(GossipParams, need_norm), TAB_FIELDS(GossipParams),
     PTRF2(GossipParams, fsm, thres), PTRF2(GossipParams, fsm, last_norm), PTRF2(GossipParams, fsm, last_iter),
     PTRF2(GossipParams, fsm, slopes), PTRF2(GossipParams, fsm, fire), PTRF2(GossipParams, fsm, cur_norm),
     PTRF2(GossipParams, fsm, counters), PTRF2(GossipParams, fsm, pass_num), PTRF2(GossipParams, fsm, log_ring),

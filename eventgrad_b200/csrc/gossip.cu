@@ -22,12 +22,12 @@
 namespace egb {
 
 // -------------------------------------------------------------------------------------------
-// Trigger FSM for step `next_step`, executed by ONE CTA (8 warps, one tensor per warp turn).
+// Trigger FSM update of ONE tensor for step `next_step` (scalar code, one lane).
+// Also accounts the messages of the step that just ran (fire[i] still holds that decision).
 // -------------------------------------------------------------------------------------------
-__device__ void fsm_decide(const FsmDev& f, const TableDev& tab, const float* tile_ss,
-                           const float* tile_ss_l, const float* tile_ss_r, const float* ext_norm,
-                           int next_step) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void fsm_update_tensor(const FsmDev& f, const TableDev& tab, int i, float norm,
+                                                  float lnorm, float rnorm, bool have_recv, int next_step,
+                                                  bool count) {
   const int sz = tab.n_tensors;
   float* row_next = nullptr;   // log row of the decision (step next_step)
   float* row_cur = nullptr;    // log row of the step that just ran (receive-side norms)
@@ -35,83 +35,92 @@ __device__ void fsm_decide(const FsmDev& f, const TableDev& tab, const float* ti
     row_next = f.log_ring + (size_t)((next_step - 1) % f.log_cap) * sz * 5;
     if (next_step >= 2) row_cur = f.log_ring + (size_t)((next_step - 2) % f.log_cap) * sz * 5;
   }
-  for (int i = warp; i < sz; i += EG_WARPS) {
-    const int ts = tab.t_tile_start[i], tc = tab.t_tile_count[i];
-    double acc = 0.0, accl = 0.0, accr = 0.0;
-    if (ext_norm == nullptr) {
-      const int beg = ts * EG_WARPS, end = (ts + tc) * EG_WARPS;
-      for (int j = beg + lane; j < end; j += 32) {
-        acc += (double)__ldcg(tile_ss + j);
-        if (row_cur != nullptr && tile_ss_l != nullptr) {
-          accl += (double)__ldcg(tile_ss_l + j);
-          accr += (double)__ldcg(tile_ss_r + j);
-        }
-      }
-      acc = warp_sum_d(acc);
-      accl = warp_sum_d(accl);
-      accr = warp_sum_d(accr);
-    }
-    if (lane == 0) {
-      const float norm = ext_norm ? ext_norm[i] : (float)sqrt(acc);
-      if (row_cur != nullptr && tile_ss_l != nullptr) {
-        row_cur[i * 5 + 3] = (float)sqrt(accl);
-        row_cur[i * 5 + 4] = (float)sqrt(accr);
-      }
-      f.cur_norm[i] = norm;
-      if (f.enabled) {
-        const float value_diff = fabsf(__fsub_rn(norm, f.last_norm[i]));
-        const float iter_diff = __fsub_rn((float)next_step, f.last_iter[i]);
-        float th = (f.thres_type == 1) ? __fmul_rn(f.thres[i], f.horizon) : f.constant;
-        const bool fire = (value_diff >= th) || (next_step < f.initial_comm_passes);
-        if (row_next != nullptr) {
-          row_next[i * 5 + 0] = norm;
-          row_next[i * 5 + 1] = th;
-          row_next[i * 5 + 2] = fire ? 1.f : 0.f;
-        }
-        if (fire) {
-          const int H = f.history;
-          float* sl = f.slopes + (size_t)i * H;
-          double avg = 0.0;
-          for (int j = 0; j < H - 1; ++j) {
-            sl[j] = sl[j + 1];
-            avg += (double)sl[j];
-          }
-          sl[H - 1] = __fdiv_rn(value_diff, iter_diff);
-          avg += (double)sl[H - 1];
-          avg /= (double)H;
-          if (f.thres_type == 1) th = (float)avg;
-          f.last_norm[i] = norm;
-          f.last_iter[i] = (float)next_step;
-        }
-        f.thres[i] = th;
-        f.fire[i] = fire ? 1 : 0;
-      }
-    }
+  if (row_cur != nullptr && have_recv) {
+    row_cur[i * 5 + 3] = lnorm;
+    row_cur[i * 5 + 4] = rnorm;
   }
+  f.cur_norm[i] = norm;
+  if (!f.enabled) return;
+  if (count && f.fire[i]) {   // +2 events per fired tensor, one per ring neighbour (event.cpp:319)
+    atomicAdd(f.counters + 0, 2ull);
+    atomicAdd(f.counters + 1, 2ull * (unsigned long long)tab.t_msg_bytes[i]);
+    atomicAdd(f.counters + 2, 1ull);
+  }
+  const float value_diff = fabsf(__fsub_rn(norm, f.last_norm[i]));
+  const float iter_diff = __fsub_rn((float)next_step, f.last_iter[i]);
+  float th = (f.thres_type == 1) ? __fmul_rn(f.thres[i], f.horizon) : f.constant;
+  const bool fire = (value_diff >= th) || (next_step < f.initial_comm_passes);
+  if (row_next != nullptr) {
+    row_next[i * 5 + 0] = norm;
+    row_next[i * 5 + 1] = th;
+    row_next[i * 5 + 2] = fire ? 1.f : 0.f;
+  }
+  if (fire) {
+    const int H = f.history;
+    float* sl = f.slopes + (size_t)i * H;
+    double avg = 0.0;
+    for (int j = 0; j < H - 1; ++j) {
+      sl[j] = sl[j + 1];
+      avg += (double)sl[j];
+    }
+    sl[H - 1] = __fdiv_rn(value_diff, iter_diff);
+    avg += (double)sl[H - 1];
+    avg /= (double)H;
+    if (f.thres_type == 1) th = (float)avg;
+    f.last_norm[i] = norm;
+    f.last_iter[i] = (float)next_step;
+  }
+  f.thres[i] = th;
+  f.fire[i] = fire ? 1 : 0;
 }
 
-// Account the messages of the step that just ran: +2 events per fired tensor (one per ring
-// neighbour, event.cpp:319) and the payload bytes that crossed NVLink.
-__device__ void count_events(const FsmDev& f, const TableDev& tab) {
-  if (!f.enabled) return;
-  unsigned long long ev = 0, by = 0, nf = 0;
-  for (int i = threadIdx.x; i < tab.n_tensors; i += EG_THREADS) {
-    if (f.fire[i]) {
-      ev += 2;
-      by += 2ull * (unsigned long long)tab.t_msg_bytes[i];
-      nf += 1;
-    }
+// Fixed-order reduction of the per-warp partials of one tensor by ONE warp: every lane owns a
+// strided subsequence (float4 loads, 4 independent accumulators), then a shuffle tree.
+__device__ __forceinline__ double reduce_partials(const float* part, int n4, int lane) {
+  const float4* p4 = reinterpret_cast<const float4*>(part);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = lane;
+  for (; j + 96 < n4; j += 128) {
+    const float4 x0 = __ldcg(p4 + j), x1 = __ldcg(p4 + j + 32), x2 = __ldcg(p4 + j + 64), x3 = __ldcg(p4 + j + 96);
+    a0 += ((double)x0.x + (double)x0.y) + ((double)x0.z + (double)x0.w);
+    a1 += ((double)x1.x + (double)x1.y) + ((double)x1.z + (double)x1.w);
+    a2 += ((double)x2.x + (double)x2.y) + ((double)x2.z + (double)x2.w);
+    a3 += ((double)x3.x + (double)x3.y) + ((double)x3.z + (double)x3.w);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ev += __shfl_xor_sync(0xffffffffu, ev, o);
-    by += __shfl_xor_sync(0xffffffffu, by, o);
-    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  for (; j < n4; j += 32) {
+    const float4 x0 = __ldcg(p4 + j);
+    a0 += ((double)x0.x + (double)x0.y) + ((double)x0.z + (double)x0.w);
   }
-  if ((threadIdx.x & 31) == 0 && ev) {
-    atomicAdd(f.counters + 0, ev);
-    atomicAdd(f.counters + 1, by);
-    atomicAdd(f.counters + 2, nf);
+  return warp_sum_d((a0 + a1) + (a2 + a3));
+}
+
+// Called by every warp after it has written its partial(s) of tile t (tensor i).  The warp that
+// completes the tensor (all tile_count*8 partials present) reduces them and runs the trigger --
+// so the FSM work is spread over the grid and overlaps the streaming of the other tensors
+// instead of forming a serial tail.
+__device__ __forceinline__ void tensor_finish(const GossipParams& p, int i, int lane, int next_step,
+                                              bool count, bool recv_ok = true) {
+  unsigned done = 0;
+  if (lane == 0) {
+    __threadfence();
+    done = atomicAdd(p.tensor_done + i, 1u);
+  }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  const unsigned total = (unsigned)p.tab.t_tile_count[i] * EG_WARPS;
+  if (done != total - 1) return;
+  __threadfence();
+  const size_t off = (size_t)p.tab.t_tile_start[i] * EG_WARPS;
+  const int n4 = (int)(total / 4);
+  const double ss = reduce_partials(p.tile_ss + off, n4, lane);
+  double sl = 0.0, sr = 0.0;
+  const bool recv = recv_ok && (p.tile_ss_l != nullptr);
+  if (recv) {
+    sl = reduce_partials(p.tile_ss_l + off, n4, lane);
+    sr = reduce_partials(p.tile_ss_r + off, n4, lane);
+  }
+  if (lane == 0) {
+    p.tensor_done[i] = 0u;
+    fsm_update_tensor(p.fsm, p.tab, i, (float)sqrt(ss), (float)sqrt(sl), (float)sqrt(sr), recv, next_step, count);
   }
 }
 
@@ -129,12 +138,18 @@ __device__ __forceinline__ void push_tile(const GossipParams& p, size_t base, co
 // mix + SGD + norm-on-write for one tile. `th` already holds theta_k for this thread's 8 floats.
 template <bool kMom>
 __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t base, F8 th, int lane,
-                                         int warp) {
+                                         int warp, int step) {
   const bool logrecv = (p.tile_ss_l != nullptr);
   float ssl = 0.f, ssr = 0.f;
+  // issue every load of the tile before the first dependent FP op (5 x 32 B in flight per lane)
+  F8 L, R, m;
   if (p.do_mix) {
-    const F8 L = ld_f8_cg(p.inbox_l + base);
-    const F8 R = ld_f8_cg(p.inbox_r + base);
+    L = ld_f8_cg(p.inbox_l + base);
+    R = ld_f8_cg(p.inbox_r + base);
+  }
+  const F8 g = ld_f8(p.grad + base);
+  if (kMom) m = ld_f8(p.mom + base);
+  if (p.do_mix) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       th.v[e] = __fdiv_rn(__fadd_rn(__fadd_rn(th.v[e], L.v[e]), R.v[e]), 3.0f);
@@ -144,10 +159,8 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
       }
     }
   }
-  const F8 g = ld_f8(p.grad + base);
   float ss = 0.f;
   if (kMom) {
-    F8 m = ld_f8(p.mom + base);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       m.v[e] = __fadd_rn(__fmul_rn(m.v[e], p.mu), g.v[e]);
@@ -175,6 +188,7 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
     ssl = warp_sum(ssl);
     ssr = warp_sum(ssr);
   }
+  if (!p.need_norm) return;
   if (lane == 0) {
     p.tile_ss[(size_t)t * EG_WARPS + warp] = ss;
     if (logrecv) {
@@ -182,9 +196,11 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
       p.tile_ss_r[(size_t)t * EG_WARPS + warp] = ssr;
     }
   }
+  tensor_finish(p, p.tab.tile_tensor[t], lane, step + 1, p.do_mix != 0);
 }
 
-// Elect the last CTA of the grid; it runs the FSM for step+1, acks, and bumps the step counter.
+// Elect the last CTA of the grid; it acks and bumps the step counter (the trigger FSM itself is
+// run per tensor by whichever warp completes that tensor, see tensor_finish).
 __device__ __forceinline__ void grid_tail(const GossipParams& p, int step) {
   __shared__ int s_last;
   __syncthreads();
@@ -195,11 +211,6 @@ __device__ __forceinline__ void grid_tail(const GossipParams& p, int step) {
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
-  if (p.do_mix) count_events(p.fsm, p.tab);
-  __syncthreads();
-  fsm_decide(p.fsm, p.tab, p.tile_ss, p.tile_ss_l, p.tile_ss_r, nullptr, step + 1);
-  __syncthreads();
   if (threadIdx.x == 0) {
     *p.ticket = 0u;
     *p.fsm.pass_num = step;
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
       const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
       const F8 th = ld_f8(p.theta + base);
       if (push && p.fsm.fire[p.tab.tile_tensor[t]]) push_tile(p, base, th);
-      mix_tile<kMom>(p, t, base, th, lane, warp);
+      mix_tile<kMom>(p, t, base, th, lane, warp, step);
     }
   } else {
     // ---------------- iter-sync: software-pipelined push(q) | wait+mix(q-1) -----------------
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
           const int t = b + j * G;
           if (t < n_tiles) {
             const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
-            mix_tile<kMom>(p, t, base, ld_f8(p.theta + base), lane, warp);
+            mix_tile<kMom>(p, t, base, ld_f8(p.theta + base), lane, warp, step);
           }
         }
       }
@@ -283,6 +294,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
 __global__ void __launch_bounds__(EG_THREADS, 4) gossip_init_kernel(const GossipParams p, int run_fsm) {
   const int b = blockIdx.x, G = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int next_step = *p.fsm.pass_num + 1;
   for (int t = b; t < p.tab.n_tiles; t += G) {
     const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
     const F8 th = ld_f8(p.theta + base);
@@ -291,26 +303,23 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_init_kernel(const Gossip
     for (int e = 0; e < 8; ++e) ss = __fmaf_rn(th.v[e], th.v[e], ss);
     if (p.shadow != nullptr) st_bf16x8(p.shadow + base, th);
     ss = warp_sum(ss);
-    if (lane == 0) p.tile_ss[(size_t)t * EG_WARPS + warp] = ss;
+    if (lane == 0) {
+      p.tile_ss[(size_t)t * EG_WARPS + warp] = ss;
+      if (p.tile_ss_l != nullptr) {
+        p.tile_ss_l[(size_t)t * EG_WARPS + warp] = 0.f;
+        p.tile_ss_r[(size_t)t * EG_WARPS + warp] = 0.f;
+      }
+    }
+    if (run_fsm) tensor_finish(p, p.tab.tile_tensor[t], lane, next_step, false, /*recv_ok=*/false);
   }
-  __shared__ int s_last;
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned prev = atomicAdd(p.ticket, 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (run_fsm) fsm_decide(p.fsm, p.tab, p.tile_ss, nullptr, nullptr, nullptr, *p.fsm.pass_num + 1);
-  __syncthreads();
-  if (tid == 0) *p.ticket = 0u;
 }
 
+// Trigger FSM alone, norms supplied by the caller (unit test against parallel/trigger.py).
 __global__ void __launch_bounds__(EG_THREADS) fsm_decide_kernel(const FsmDev f, const TableDev t,
                                                                const float* ext_norm) {
-  fsm_decide(f, t, nullptr, nullptr, nullptr, ext_norm, *f.pass_num + 1);
+  const int next_step = *f.pass_num + 1;
+  for (int i = threadIdx.x; i < t.n_tensors; i += EG_THREADS)
+    fsm_update_tensor(f, t, i, ext_norm[i], 0.f, 0.f, false, next_step, false);
   __syncthreads();
   if (threadIdx.x == 0) *f.pass_num += 1;
 }

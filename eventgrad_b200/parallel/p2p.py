@@ -124,6 +124,7 @@ class P2PBackend(CommBackend):
         self.ticket = zi(4)
         self.status = zi(1)
         self.tile_ss = zf(t.n_tiles * 8)
+        self.tensor_done = zi(t.n_tensors)
         self.log_cap = 0
         self.log_ring = None
         self.tile_ss_l = self.tile_ss_r = None
@@ -178,8 +179,10 @@ class P2PBackend(CommBackend):
             gp.update({
                 "theta": P(a.theta), "grad": P(a.grad), "mom": P(a.mom) if cfg.momentum != 0 else 0,
                 "tile_ss": P(self.tile_ss), "tile_ss_l": P(self.tile_ss_l), "tile_ss_r": P(self.tile_ss_r),
-                "ticket": P(self.ticket), "status": P(self.status), "timeout_ns": int(self.timeout_ns),
+                "ticket": P(self.ticket), "tensor_done": P(self.tensor_done), "status": P(self.status),
+                "timeout_ns": int(self.timeout_ns),
                 "lr": float(cfg.lr), "mu": float(cfg.momentum),
+                "need_norm": 1 if (cfg.algo in ("event", "spevent") or self.log_ring is not None) else 0,
                 "do_mix": 1 if self.do_comm else 0,
                 "do_push": 1 if (self.do_comm and dense) else 0,
                 "sync": 1 if self.sync else 0,

@@ -103,7 +103,11 @@ def main():
             sim.step([grad_of(s, r) for r in range(W)], fires=fo)
         for r in range(W):
             got = allth[r].cpu()
-            if a.sync_mode == "iter" and a.algo != "cent":
+            if a.sync_mode == "async":
+                # reference RMA semantics: neighbours' values may be one step stale or newer, so the
+                # trajectory is timing dependent -- only sanity is checked (finite, near the oracle)
+                same = bool(torch.isfinite(got).all()) and float((got - sim.theta[r]).abs().max()) < 0.5
+            elif a.algo != "cent":
                 same = torch.equal(got, sim.theta[r])
             else:
                 same = torch.allclose(got, sim.theta[r], rtol=1e-5, atol=1e-6)
