@@ -1,0 +1,50 @@
+"""CPU multi-process tests (gloo, world_size 2-4): the real driver + backend abstraction with no
+GPU (BASELINE config 1 and SURVEY.md section 4 item 2). Workers compare against the simulator."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PORT = [29900 + (os.getpid() % 50) * 10]
+
+
+def _torchrun(world, script, *args, timeout=300):
+    _PORT[0] += 1
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_PORT[0]), *script, *args]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
+    return r.returncode, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("algo,world", [("cent", 2), ("decent", 3), ("event", 2), ("event", 4), ("spevent", 3)])
+def test_collective_backend_matches_simulator(algo, world):
+    rc, out = _torchrun(world, [os.path.join(ROOT, "tests", "dist_worker.py")], "--algo", algo,
+                        "--backend", "gloo", "--steps", "10")
+    assert rc == 0 and "WORKER_OK" in out, out[-2000:]
+
+
+def test_cent_program_end_to_end_world2(tmp_path):
+    """BASELINE config 1: dmnist/cent AllReduce MLP on CPU/gloo world_size=2."""
+    rc, out = _torchrun(2, ["-m", "eventgrad_b200.cli.cent"], "--epochs", "6", "--train-samples", "2000",
+                        "--test-samples", "400", "--device", "cpu")
+    assert rc == 0, out[-2000:]
+    assert "Number of parameters - 4" in out and "Number of elements - 101770" in out
+    assert "Training time - " in out and "Test Accuracy - " in out
+    accs = [float(l.split(", ")[1]) for l in out.splitlines() if l.startswith("6, ")]
+    first = [float(l.split(", ")[1]) for l in out.splitlines() if l.startswith("1, ")]
+    assert len(accs) == 2 and min(accs) > max(first)               # it learns, on every rank
+
+
+def test_mnist_event_program_logs_and_counts(tmp_path):
+    rc, out = _torchrun(2, ["-m", "eventgrad_b200.cli.mnist_event"], "1", "1", "0.95", "--epochs", "1",
+                        "--train-samples", "2048", "--test-samples", "256", "--device", "cpu",
+                        "--log-dir", str(tmp_path))
+    assert rc == 0, out[-2000:]
+    assert "Total number of events - " in out and out.count("No of events in rank") == 2
+    send = open(tmp_path / "send0.txt").read().splitlines()
+    assert len(send) == 16                                          # ceil(1024/64) steps
+    assert len(send[0].split(",  ")) == 8 * 3 + 1                   # norm, thres, fired per tensor
+    assert os.path.exists(tmp_path / "recv1.txt")
