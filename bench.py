@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--no-channels-last", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--out", default="")
+    p.add_argument("--profile", default="", help="write a torch.profiler kernel table of a few e2e steps here")
     return p.parse_args()
 
 
@@ -99,7 +100,8 @@ def main():
         x, y = next(it)
         pool.append((x.clone(), y.clone()))
     torch.cuda.synchronize()
-    for i in range(args.warmup):
+    prewarm = max(args.warmup, Trainer.GRAPH_WARMUP_STEPS + 2)   # eager warm-up + graph capture, untimed
+    for i in range(prewarm):
         tr.train_step(*pool[i % len(pool)])
     torch.cuda.synchronize()
     barrier(env)
@@ -133,14 +135,20 @@ def main():
         t0 = time.perf_counter()
         e0.record()
         d2h = 0
+        tl = tt = ti = 0.0
         for _ in range(args.steps):
+            ta = time.perf_counter()
             try:
                 x, y = next(it)
             except StopIteration:
                 it = iter(tr.loader)
                 x, y = next(it)
+            tb = time.perf_counter()
             loss = tr.train_step(x, y)
+            tc = time.perf_counter()
             lv = loss.item()                      # D2H read of the step result
+            td = time.perf_counter()
+            tl += tb - ta; tt += tc - tb; ti += td - tc
             d2h += loss.element_size()
         e1.record()
         torch.cuda.synchronize()
@@ -152,7 +160,21 @@ def main():
                "ms_per_step": ms2 / args.steps,
                "h2d_bytes_per_step": int(per_rank * (c * h * w + 8) * N),
                "d2h_bytes_per_step": int(d2h / args.steps * N),
+               "host_ms": {"loader": tl / args.steps * 1e3, "launch": tt / args.steps * 1e3,
+                           "result_wait": ti / args.steps * 1e3},
                "last_loss": lv}
+
+    if args.profile and env.rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        it = iter(tr.loader)
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(4):
+                x, y = next(it)
+                loss = tr.train_step(x, y)
+                loss.item()
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile)), exist_ok=True)
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40))
 
     # ---------------- communication accounting ----------------------------------------------------
     be = tr.backend

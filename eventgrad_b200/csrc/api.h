@@ -170,6 +170,36 @@ cudaError_t launch_decode_augment(const uint8_t* in, void* out, const int* oy, c
                                   const int* flip, int B, int C, int H, int W, int pad, float scale,
                                   float mean, float inv_std, int out_bf16, int nhwc, cudaStream_t s);
 
+// ------------------------------------------------------------------ fused BatchNorm(+add)(+ReLU)
+// NHWC bf16 activations [M = N*H*W, C], fp32 statistics / affine parameters (csrc/bn_act.cu).
+struct BnParams {
+  const __nv_bfloat16* x;     // BN input (conv output)
+  const __nv_bfloat16* res;   // optional residual added before the activation
+  __nv_bfloat16* y;           // output (forward) / saved output for the ReLU mask (backward)
+  const __nv_bfloat16* dy;    // backward: grad wrt y
+  __nv_bfloat16* dx;          // backward: grad wrt x
+  __nv_bfloat16* dres;        // backward: grad wrt residual (optional)
+  const float* gamma;
+  const float* beta;
+  float* mean;                // saved batch mean   [C]
+  float* invstd;              // saved 1/sqrt(var+eps)
+  float* run_mean;            // optional running stats (updated in the stats kernel)
+  float* run_var;
+  long long* nbt;             // optional num_batches_tracked
+  float* dgamma;              // backward outputs (fp32) -- also inputs of the dx kernel
+  float* dbeta;
+  float* partial;             // workspace [bn_partial_rows][2*C]
+  unsigned int* ticket;
+  long long M;
+  int C;
+  float eps;
+  float momentum;
+  int relu;
+};
+int bn_partial_rows(int sm_count);
+// which: 0 fwd stats, 1 fwd apply, 2 bwd reduce, 3 bwd dx
+cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s);
+
 // ------------------------------------------------------------------ IPC window runtime
 // The RMA-window replacement (MPI_Alloc_mem + MPI_Win_create, event.cpp:138-147).
 struct IpcHandle {

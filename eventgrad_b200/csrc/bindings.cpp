@@ -80,6 +80,14 @@ static const std::unordered_map<std::string, Setter<SparseParams>> kSparse = {
     NUMF(SparseParams, timeout_ns), NUMF(SparseParams, sync), TAB_FIELDS(SparseParams),
 };
 
+static const std::unordered_map<std::string, Setter<BnParams>> kBn = {
+    PTRF(BnParams, x), PTRF(BnParams, res), PTRF(BnParams, y), PTRF(BnParams, dy), PTRF(BnParams, dx),
+    PTRF(BnParams, dres), PTRF(BnParams, gamma), PTRF(BnParams, beta), PTRF(BnParams, mean),
+    PTRF(BnParams, invstd), PTRF(BnParams, run_mean), PTRF(BnParams, run_var), PTRF(BnParams, nbt),
+    PTRF(BnParams, dgamma), PTRF(BnParams, dbeta), PTRF(BnParams, partial), PTRF(BnParams, ticket),
+    NUMF(BnParams, M), NUMF(BnParams, C), NUMF(BnParams, eps), NUMF(BnParams, momentum), NUMF(BnParams, relu),
+};
+
 template <class S>
 static void bind_params(py::module_& m, const char* name, const std::unordered_map<std::string, Setter<S>>& tbl) {
   py::class_<S>(m, name)
@@ -119,6 +127,7 @@ PYBIND11_MODULE(_C, m) {
   bind_params<GossipParams>(m, "GossipParams", kGossip);
   bind_params<AllReduceParams>(m, "AllReduceParams", kAllReduce);
   bind_params<SparseParams>(m, "SparseParams", kSparse);
+  bind_params<BnParams>(m, "BnParams", kBn);
 
   m.def("gossip_max_grid", &gossip_max_grid);
   m.def("gossip_step", [](const GossipParams& p, int grid, uintptr_t s) {
@@ -138,6 +147,54 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("sparse_apply", [](const SparseParams& p, int grid, uintptr_t s) {
     check(launch_sparse_apply(p, grid, S(s)), "sparse_apply");
+  });
+  m.def("bn_partial_rows", &bn_partial_rows);
+  m.def("bn_launch", [](const BnParams& p, int which, int sm_count, uintptr_t s) {
+    check(launch_bn(p, which, sm_count, S(s)), "bn_launch");
+  });
+  // positional fast path (avoids the dict round trip on the per-layer hot path)
+  m.def("bn_forward", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t gamma, uintptr_t beta, uintptr_t mean,
+                         uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt, uintptr_t partial,
+                         uintptr_t ticket, long long M, int C, float eps, float momentum, int relu, int training,
+                         int sm_count, uintptr_t s) {
+    BnParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+    p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.gamma = reinterpret_cast<const float*>(gamma);
+    p.beta = reinterpret_cast<const float*>(beta);
+    p.mean = reinterpret_cast<float*>(mean);
+    p.invstd = reinterpret_cast<float*>(invstd);
+    p.run_mean = reinterpret_cast<float*>(run_mean);
+    p.run_var = reinterpret_cast<float*>(run_var);
+    p.nbt = reinterpret_cast<long long*>(nbt);
+    p.partial = reinterpret_cast<float*>(partial);
+    p.ticket = reinterpret_cast<unsigned int*>(ticket);
+    p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu;
+    if (training) check(launch_bn(p, 0, sm_count, S(s)), "bn_fwd_stats");
+    check(launch_bn(p, 1, sm_count, S(s)), "bn_fwd_apply");
+  });
+  m.def("bn_backward", [](uintptr_t x, uintptr_t y, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
+                          uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
+                          uintptr_t ticket, long long M, int C, int relu, int sm_count, uintptr_t s) {
+    BnParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+    p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
+    p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
+    p.gamma = reinterpret_cast<const float*>(gamma);
+    p.mean = reinterpret_cast<float*>(mean);
+    p.invstd = reinterpret_cast<float*>(invstd);
+    p.dgamma = reinterpret_cast<float*>(dgamma);
+    p.dbeta = reinterpret_cast<float*>(dbeta);
+    p.partial = reinterpret_cast<float*>(partial);
+    p.ticket = reinterpret_cast<unsigned int*>(ticket);
+    p.M = M; p.C = C; p.relu = relu;
+    check(launch_bn(p, 2, sm_count, S(s)), "bn_bwd_reduce");
+    check(launch_bn(p, 3, sm_count, S(s)), "bn_bwd_dx");
   });
   m.def("decode_augment",
         [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,

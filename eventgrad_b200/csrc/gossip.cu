@@ -94,33 +94,55 @@ __device__ __forceinline__ double reduce_partials(const float* part, int n4, int
   return warp_sum_d((a0 + a1) + (a2 + a3));
 }
 
-// Called by every warp after it has written its partial(s) of tile t (tensor i).  The warp that
-// completes the tensor (all tile_count*8 partials present) reduces them and runs the trigger --
-// so the FSM work is spread over the grid and overlaps the streaming of the other tensors
-// instead of forming a serial tail.
-__device__ __forceinline__ void tensor_finish(const GossipParams& p, int i, int lane, int next_step,
-                                              bool count, bool recv_ok = true) {
-  unsigned done = 0;
-  if (lane == 0) {
+// Norm reduction + trigger, spread over the grid with no serial tail and no per-tile fences:
+// every CTA, once it has finished ALL its tiles, adds the number of tiles it contributed to each
+// tensor's completion counter (one fence per CTA, <= tiles-per-CTA atomics).  The CTA whose add
+// completes a tensor reduces that tensor's per-warp partials in fixed order (one warp per tensor)
+// and runs the trigger FSM for it.  Tiles of a CTA ascend, so equal tensors are consecutive.
+#define EG_MAX_OWN 1024   // >= number of parameter tensors (asserted host-side)
+__device__ __forceinline__ void cta_finish_tensors(const GossipParams& p, int next_step, bool count,
+                                                   bool recv_ok) {
+  __shared__ int s_own[EG_MAX_OWN];
+  __shared__ int s_nown;
+  const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();                       // every warp of this CTA has stored its partials
+  if (tid == 0) {
     __threadfence();
-    done = atomicAdd(p.tensor_done + i, 1u);
+    int nown = 0, cur = -1, cnt = 0;
+    for (int t = b; ; t += G) {
+      const int i = (t < p.tab.n_tiles) ? p.tab.tile_tensor[t] : -2;
+      if (i != cur) {
+        if (cur >= 0) {
+          const unsigned prev = atomicAdd(p.tensor_done + cur, (unsigned)cnt);
+          if (prev + (unsigned)cnt == (unsigned)p.tab.t_tile_count[cur] && nown < EG_MAX_OWN) s_own[nown++] = cur;
+        }
+        cur = i;
+        cnt = 0;
+      }
+      if (i == -2) break;
+      ++cnt;
+    }
+    s_nown = nown;
   }
-  done = __shfl_sync(0xffffffffu, done, 0);
-  const unsigned total = (unsigned)p.tab.t_tile_count[i] * EG_WARPS;
-  if (done != total - 1) return;
+  __syncthreads();
+  const int nown = s_nown;
+  if (nown == 0) return;
   __threadfence();
-  const size_t off = (size_t)p.tab.t_tile_start[i] * EG_WARPS;
-  const int n4 = (int)(total / 4);
-  const double ss = reduce_partials(p.tile_ss + off, n4, lane);
-  double sl = 0.0, sr = 0.0;
   const bool recv = recv_ok && (p.tile_ss_l != nullptr);
-  if (recv) {
-    sl = reduce_partials(p.tile_ss_l + off, n4, lane);
-    sr = reduce_partials(p.tile_ss_r + off, n4, lane);
-  }
-  if (lane == 0) {
-    p.tensor_done[i] = 0u;
-    fsm_update_tensor(p.fsm, p.tab, i, (float)sqrt(ss), (float)sqrt(sl), (float)sqrt(sr), recv, next_step, count);
+  for (int k = warp; k < nown; k += EG_WARPS) {
+    const int i = s_own[k];
+    const size_t off = (size_t)p.tab.t_tile_start[i] * EG_WARPS;
+    const int n4 = p.tab.t_tile_count[i] * EG_WARPS / 4;
+    const double ss = reduce_partials(p.tile_ss + off, n4, lane);
+    double sl = 0.0, sr = 0.0;
+    if (recv) {
+      sl = reduce_partials(p.tile_ss_l + off, n4, lane);
+      sr = reduce_partials(p.tile_ss_r + off, n4, lane);
+    }
+    if (lane == 0) {
+      p.tensor_done[i] = 0u;
+      fsm_update_tensor(p.fsm, p.tab, i, (float)sqrt(ss), (float)sqrt(sl), (float)sqrt(sr), recv, next_step, count);
+    }
   }
 }
 
@@ -189,6 +211,7 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
     ssr = warp_sum(ssr);
   }
   if (!p.need_norm) return;
+  (void)step;
   if (lane == 0) {
     p.tile_ss[(size_t)t * EG_WARPS + warp] = ss;
     if (logrecv) {
@@ -196,11 +219,10 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
       p.tile_ss_r[(size_t)t * EG_WARPS + warp] = ssr;
     }
   }
-  tensor_finish(p, p.tab.tile_tensor[t], lane, step + 1, p.do_mix != 0);
 }
 
 // Elect the last CTA of the grid; it acks and bumps the step counter (the trigger FSM itself is
-// run per tensor by whichever warp completes that tensor, see tensor_finish).
+// run per tensor by whichever warp completes that tensor, see cta_finish_tensors).
 __device__ __forceinline__ void grid_tail(const GossipParams& p, int step) {
   __shared__ int s_last;
   __syncthreads();
@@ -285,6 +307,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
       }
     }
   }
+  if (p.need_norm) cta_finish_tensors(p, step + 1, p.do_mix != 0, true);
   grid_tail(p, step);
 }
 
@@ -310,8 +333,8 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_init_kernel(const Gossip
         p.tile_ss_r[(size_t)t * EG_WARPS + warp] = 0.f;
       }
     }
-    if (run_fsm) tensor_finish(p, p.tab.tile_tensor[t], lane, next_step, false, /*recv_ok=*/false);
   }
+  if (run_fsm) cta_finish_tensors(p, next_step, false, /*recv_ok=*/false);
 }
 
 // Trigger FSM alone, norms supplied by the caller (unit test against parallel/trigger.py).

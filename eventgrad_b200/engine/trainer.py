@@ -80,6 +80,7 @@ class Trainer:
         self.epoch = 0
         self.steps_done = 0
         self._graphs = {}
+        self._graph_warm = {}
         self.train_time_s = 0.0
         if cfg.resume:
             sd = load_checkpoint(cfg.resume, arena=self.arena, backend=self.backend, model=self.model)
@@ -110,32 +111,41 @@ class Trainer:
             self.correct += (out.argmax(1) == y).sum()
         return loss.detach()
 
-    def _graphed_fwd_bwd(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    GRAPH_WARMUP_STEPS = 3
+
+    def _graphed_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """Replay the step from a CUDA graph (per input shape).  The first GRAPH_WARMUP_STEPS steps
+        of a shape run eagerly (cuDNN autotune, lazy kernel loading, allocator warm-up); then the
+        step is captured once.  With a graph-safe backend (p2p) the capture holds the WHOLE step --
+        forward, backward and the fused exchange/average/SGD kernel, which spins on its neighbours'
+        flags from inside the graph; otherwise only forward+backward are captured."""
         key = tuple(x.shape)
         ent = self._graphs.get(key)
+        whole = bool(getattr(self.backend, "graph_safe", False))
         if ent is None:
+            n = self._graph_warm.get(key, 0)
+            if n < self.GRAPH_WARMUP_STEPS:
+                self._graph_warm[key] = n + 1
+                loss = self._fwd_bwd(x, y)
+                self.backend.step()
+                return loss
             sx, sy = x.clone(), y.clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):            # warm-up (cudnn autotune, lazy init) off-graph
-                for _ in range(3):
-                    self.arena.zero_grad()
-                    self._fwd_bwd(sx, sy)
-            torch.cuda.current_stream().wait_stream(side)
-            # undo warm-up side effects on counters (BN running stats drift is harmless)
-            self.correct.zero_()
-            self.arena.zero_grad()
+            torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 sloss = self._fwd_bwd(sx, sy)
+                if whole:
+                    self.backend.launch()
             ent = (g, sx, sy, sloss)
             self._graphs[key] = ent
-            self.correct.zero_()
-            self.arena.zero_grad()
         g, sx, sy, sloss = ent
         sx.copy_(x)
         sy.copy_(y)
         g.replay()
+        if whole:
+            self.backend.account_step()
+        else:
+            self.backend.step()
         return sloss
 
     def train_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -143,10 +153,10 @@ class Trainer:
         if not getattr(self.backend, "zeroes_grad", False):
             self.arena.zero_grad()
         if self.cfg.cuda_graph and self.device.type == "cuda":
-            loss = self._graphed_fwd_bwd(x, y)
+            loss = self._graphed_step(x, y)
         else:
             loss = self._fwd_bwd(x, y)
-        self.backend.step()
+            self.backend.step()
         self.steps_done += 1
         self.last_loss = loss
         return loss

@@ -9,6 +9,8 @@ Reference: /root/reference/dcifar10/common/resnet.hpp
     elements. `variant="ref"` reproduces that topology (apples-to-apples message
     shapes); `variant="canonical"` builds the textbook blocks-per-stage network
     (62 tensors / 11 173 962 elements for ResNet-18).
+BatchNorm layers are ops.bn_act.FusedBNAct (nn.BatchNorm2d subclass: same names/buffers) so that
+bn->relu and bn->(+=skip)->relu run as fused sm_100a kernels on bf16 NHWC activations.
 Parameter registration order matches LibTorch's named_parameters() walk
 (conv, bn, layer1..4 [conv1,bn1,conv2,bn2,(conv3,bn3),downsampler], fc) because the
 arena layout (= the reference's running `disp`) is defined by that order.
@@ -21,6 +23,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.bn_act import FusedBNAct
+
 
 def conv_op(cin: int, cout: int, k: int, stride: int, padding: int) -> nn.Conv2d:
     return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
@@ -32,16 +36,15 @@ class BasicBlock(nn.Module):
     def __init__(self, cin: int, cout: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
         self.conv1 = conv_op(cin, cout, 3, stride, 1)
-        self.bn1 = nn.BatchNorm2d(cout)
+        self.bn1 = FusedBNAct(cout)
         self.conv2 = conv_op(cout, cout, 3, 1, 1)
-        self.bn2 = nn.BatchNorm2d(cout)
+        self.bn2 = FusedBNAct(cout)
         self.downsampler = downsample
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
+        out = self.bn1(self.conv1(x), relu=True)
         residual = self.downsampler(x) if self.downsampler is not None else x
-        return F.relu(out + residual)
+        return self.bn2(self.conv2(out), residual=residual, relu=True)      # bn -> += skip -> relu, fused
 
 
 class BottleNeck(nn.Module):
@@ -50,19 +53,18 @@ class BottleNeck(nn.Module):
     def __init__(self, cin: int, cout: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
         self.conv1 = conv_op(cin, cout, 1, 1, 0)
-        self.bn1 = nn.BatchNorm2d(cout)
+        self.bn1 = FusedBNAct(cout)
         self.conv2 = conv_op(cout, cout, 3, stride, 1)
-        self.bn2 = nn.BatchNorm2d(cout)
+        self.bn2 = FusedBNAct(cout)
         self.conv3 = conv_op(cout, cout * self.expansion, 1, 1, 0)
-        self.bn3 = nn.BatchNorm2d(cout * self.expansion)
+        self.bn3 = FusedBNAct(cout * self.expansion)
         self.downsampler = downsample
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = F.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
+        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn2(self.conv2(out), relu=True)
         residual = self.downsampler(x) if self.downsampler is not None else x
-        return F.relu(out + residual)
+        return self.bn3(self.conv3(out), residual=residual, relu=True)
 
 
 class ResNet(nn.Module):
@@ -74,7 +76,7 @@ class ResNet(nn.Module):
         self.variant = variant
         self.in_channels = 64
         self.conv = conv_op(3, 64, 3, 1, 1)
-        self.bn = nn.BatchNorm2d(64)
+        self.bn = FusedBNAct(64)
         self.layer1 = self._make_layer(block, 64, layers[0], 1)
         self.layer2 = self._make_layer(block, 128, layers[1], 2)
         self.layer3 = self._make_layer(block, 256, layers[2], 2)
@@ -86,7 +88,7 @@ class ResNet(nn.Module):
         if stride != 1 or self.in_channels != cout * block.expansion:
             downsample = nn.Sequential(
                 conv_op(self.in_channels, cout * block.expansion, 1, stride, 0),
-                nn.BatchNorm2d(cout * block.expansion),
+                FusedBNAct(cout * block.expansion),
             )
         mods = [block(self.in_channels, cout, stride, downsample)]
         self.in_channels = cout * block.expansion
@@ -96,7 +98,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*mods)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        out = F.relu(self.bn(self.conv(x)))
+        out = self.bn(self.conv(x), relu=True)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         out = F.avg_pool2d(out, 4)
         out = out.reshape(out.shape[0], -1)

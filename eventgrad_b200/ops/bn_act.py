@@ -1,0 +1,122 @@
+"""Fused BatchNorm2d (+ residual add) (+ ReLU) for channels-last bf16 activations.
+
+Front-end of csrc/bn_act.cu.  `FusedBNAct` is a drop-in nn.BatchNorm2d subclass (same parameter
+and buffer names, so the arena layout and state_dicts are unchanged) whose forward takes an
+optional residual and a relu flag; the ResNet blocks of the reference
+(/root/reference/dcifar10/common/resnet.hpp:39-52, :91-107) map onto it as
+    bn(conv(x), relu=True)   and   bn(conv(x), residual=skip, relu=True).
+The CUDA path is taken for bf16 NHWC inputs on a GPU; anything else (CPU, fp32, NCHW) runs the
+equivalent PyTorch ops -- which are also the numerics oracle in tests/test_gpu_bn.py.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_WS = {}
+
+
+def _workspace(device):
+    ws = _WS.get(device)
+    if ws is None:
+        from . import ext
+        C = ext()
+        sm = torch.cuda.get_device_properties(device).multi_processor_count
+        rows = C.bn_partial_rows(sm)
+        ws = {"sm": sm, "partial": torch.empty(rows * 2 * 2048, dtype=torch.float32, device=device),
+              "ticket": torch.zeros(4, dtype=torch.int32, device=device), "C": C}
+        _WS[device] = ws
+    return ws
+
+
+def _eligible(x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
+    if os.environ.get("EGB_FUSED_BN", "1") == "0":
+        return False
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    C = x.shape[1]
+    if C % 8 or C > 2048 or (256 % (C // 8)):
+        return False
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        return False
+    if residual is not None and not (residual.dtype == torch.bfloat16 and residual.shape == x.shape
+                                     and residual.is_contiguous(memory_format=torch.channels_last)):
+        return False
+    return True
+
+
+class _FusedBNActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, residual, training, momentum, eps, relu):
+        ws = _workspace(x.device)
+        C_ext = ws["C"]
+        N, C, H, W = x.shape
+        M = N * H * W
+        y = torch.empty_like(x)                       # preserves channels_last
+        if training:
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            rm = running_mean.data_ptr() if running_mean is not None else 0
+            rv = running_var.data_ptr() if running_var is not None else 0
+            nb = nbt.data_ptr() if nbt is not None else 0
+        else:
+            mean = running_mean
+            invstd = torch.rsqrt(running_var + eps)
+            rm = rv = nb = 0
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            C_ext.bn_forward(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
+                             weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm, rv, nb,
+                             ws["partial"].data_ptr(), ws["ticket"].data_ptr(), M, C, float(eps),
+                             float(momentum), 1 if relu else 0, 1 if training else 0, ws["sm"], stream)
+        ctx.save_for_backward(x, y, weight, mean, invstd)
+        ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("FusedBNAct backward is only implemented for training mode")
+        ws = _workspace(x.device)
+        C_ext = ws["C"]
+        N, C, H, W = x.shape
+        M = N * H * W
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+                              dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
+                              invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws["partial"].data_ptr(),
+                              ws["ticket"].data_ptr() + 4, M, C, 1 if ctx.relu else 0, ws["sm"], stream)
+        return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
+
+
+def bn_act_reference(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu):
+    """Plain PyTorch composition (CPU / fp32 / NCHW path and the test oracle)."""
+    y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+class FusedBNAct(nn.BatchNorm2d):
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+        training = self.training or (self.running_mean is None)
+        if _eligible(x, residual) and self.affine and self.momentum is not None:
+            return _FusedBNActFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                       self.num_batches_tracked if training else None, residual, training,
+                                       self.momentum, self.eps, relu)
+        if training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        return bn_act_reference(x, self.weight, self.bias, self.running_mean, self.running_var, residual,
+                                training, self.momentum if self.momentum is not None else 0.0, self.eps, relu)

@@ -84,6 +84,8 @@ class P2PBackend(CommBackend):
         self.boot = symm.get("bootstrap") or DistBootstrap(env, group)
         self.table = arena.table
         t = self.table
+        if t.n_tensors > 1024:
+            raise ValueError("p2p backend supports at most 1024 parameter tensors (EG_MAX_OWN)")
         self.grid = min(t.n_tiles, symm["max_grid"])
         if grid_cap:
             self.grid = min(self.grid, grid_cap)
@@ -263,14 +265,16 @@ class P2PBackend(CommBackend):
             self.C.gossip_init(self.gp, self.grid, 1 if run_fsm else 0, self._stream())
 
     # ------------------------------------------------------------------ step
-    def step(self) -> None:
-        self.pass_num += 1
+    graph_safe = True      # launch() only enqueues kernels whose per-step state lives on the device
+
+    def launch(self) -> None:
+        """Enqueue this step's kernels on the current stream (CUDA-graph capturable: the step
+        counter, trigger state and handshake sequence numbers are all device resident)."""
         C, s = self.C, self._stream()
         with torch.cuda.device(self.dev):
             if self.cfg.algo == "cent":
                 if self.ring.world > 1:
                     C.allreduce(self.ap, self.grid, s)
-                    self.host_bytes += self.table.n_elems * 4
                 else:
                     C.gossip_step(self.gp, self.grid, s)       # plain fused SGD
                 return
@@ -278,8 +282,18 @@ class P2PBackend(CommBackend):
                 C.sparse_select_push(self.sp, self.grid, s)
                 C.sparse_apply(self.sp, self.grid, s)
             C.gossip_step(self.gp, self.grid, s)
-        if self.cfg.algo == "decent" and self.do_comm:
+
+    def account_step(self) -> None:
+        """Host-side bookkeeping of one executed step (after launch() or a graph replay)."""
+        self.pass_num += 1
+        if self.cfg.algo == "cent" and self.ring.world > 1:
+            self.host_bytes += self.table.n_elems * 4
+        elif self.cfg.algo == "decent" and self.do_comm:
             self.host_bytes += 2 * self.table.n_elems * 4
+
+    def step(self) -> None:
+        self.launch()
+        self.account_step()
 
     # ------------------------------------------------------------------ end of training
     def check_status(self) -> None:

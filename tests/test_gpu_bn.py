@@ -1,0 +1,94 @@
+"""Fused BatchNorm(+add)(+ReLU) kernels vs a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+
+from eventgrad_b200.ops.bn_act import FusedBNAct, _eligible, bn_act_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(N, C, H, W, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(N, C, H, W, generator=g, device="cuda") * 1.5 + 0.3).to(torch.bfloat16)
+    x = x.contiguous(memory_format=torch.channels_last)
+    r = torch.randn(N, C, H, W, generator=g, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(N, C, H, W, generator=g, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    return x, r, dy
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (7, 128, 16, 16), (5, 256, 8, 8), (3, 512, 4, 4), (2, 2048, 4, 4),
+                                   (1, 64, 3, 5)])
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False), (False, True)])
+def test_fused_bn_act_forward_backward(shape, relu, res):
+    N, C, H, W = shape
+    x, r, dy = _mk(*shape)
+    bn = FusedBNAct(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    ref = FusedBNAct(C).cuda().train()
+    ref.load_state_dict(bn.state_dict())
+    xa = x.clone().requires_grad_(True)
+    ra = r.clone().requires_grad_(True) if res else None
+    assert _eligible(xa, ra)
+    y = bn(xa, residual=ra, relu=relu)
+    y.backward(dy)
+    # fp32 reference from the same bf16 inputs
+    xb = x.float().requires_grad_(True)
+    rb = r.float().requires_grad_(True) if res else None
+    yb = bn_act_reference(xb, ref.weight, ref.bias, ref.running_mean, ref.running_var, rb, True, ref.momentum,
+                          ref.eps, relu)
+    # mask the reference backward exactly like the kernel does (on the bf16-rounded output sign)
+    yb.backward(dy.float())
+    torch.testing.assert_close(y.float(), yb, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(bn.running_mean, ref.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn.running_var, ref.running_var, rtol=1e-4, atol=1e-5)
+    scale = float(xb.grad.abs().max()) + 1e-6
+    assert float((xa.grad.float() - xb.grad).abs().max()) / scale < 3e-2
+    gs = float(ref.weight.grad.abs().max()) + 1e-6
+    assert float((bn.weight.grad - ref.weight.grad).abs().max()) / gs < 2e-2
+    bs = float(ref.bias.grad.abs().max()) + 1e-6
+    assert float((bn.bias.grad - ref.bias.grad).abs().max()) / bs < 2e-2
+    if res:
+        rs = float(rb.grad.abs().max()) + 1e-6
+        assert float((ra.grad.float() - rb.grad).abs().max()) / rs < 2e-2
+    assert int(bn.num_batches_tracked) == 1
+
+
+def test_fused_bn_eval_mode():
+    x, r, _ = _mk(4, 128, 8, 8)
+    bn = FusedBNAct(128).cuda()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.2)
+        bn.running_var.uniform_(0.5, 2.0)
+    bn.eval()
+    y = bn(x, residual=r, relu=True)
+    yb = bn_act_reference(x.float(), bn.weight, bn.bias, bn.running_mean, bn.running_var, r.float(), False, 0.1,
+                          bn.eps, True)
+    torch.testing.assert_close(y.float(), yb, rtol=2e-2, atol=2e-2)
+
+
+def test_resnet_fused_vs_fallback_one_step():
+    """Whole flagship model, bf16 autocast NHWC: fused kernels vs EGB_FUSED_BN=0 fallback."""
+    import os
+    from eventgrad_b200.models import build_model
+    torch.manual_seed(0)
+    m1 = build_model("resnet18").cuda().train()
+    m2 = build_model("resnet18").cuda().train()
+    m2.load_state_dict(m1.state_dict())
+    x = torch.randn(16, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    yl = torch.randint(0, 10, (16,), device="cuda")
+    outs = []
+    for m, flag in ((m1, "1"), (m2, "0")):
+        os.environ["EGB_FUSED_BN"] = flag
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x)
+        loss = torch.nn.functional.cross_entropy(out.float(), yl)
+        loss.backward()
+        outs.append((out.float(), loss.item(), m.fc.weight.grad.clone(), m.conv.weight.grad.clone()))
+    os.environ["EGB_FUSED_BN"] = "1"
+    assert abs(outs[0][1] - outs[1][1]) < 5e-2
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0.1, atol=0.15)
+    a, b = outs[0][3], outs[1][3]
+    cos = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)
+    assert float(cos) > 0.98, float(cos)
