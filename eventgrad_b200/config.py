@@ -61,6 +61,7 @@ class TrainConfig:
     channels_last: bool = False
     cuda_graph: bool = False
     max_steps: int = 0               # >0: stop after this many steps (tests / bench)
+    host_threads: int = 2            # intra-op CPU threads on GPU runs (0 = leave torch's default)
     # ---- observability -------------------------------------------------------
     file_write: int = 0              # reference debug files send/recv/train/values<r>.txt
     log_dir: str = "."

@@ -21,7 +21,7 @@
 namespace egb {
 
 #define BN_THREADS 256
-#define BN_UNROLL 4
+#define BN_UNROLL 8
 
 struct V8 {
   float v[8];
@@ -68,23 +68,45 @@ __device__ __forceinline__ void block_partials(const float (&a)[8], const float 
   }
 }
 
-// Last CTA: out[c] = sum_b partial[b][c] in double, fixed order, with 8 loads in flight per thread.
-// `nb` partial rows of `W` floats each.  Result broadcast through smem_d (W doubles, W <= 4096).
-__device__ __forceinline__ void final_combine(const float* partial, int nb, int W, double* out_smem) {
-  for (int c = threadIdx.x; c < W; c += BN_THREADS) {
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int b = 0;
-    for (; b + 8 <= nb; b += 8) {
-      float x[8];
+// Last CTA: out[c] = sum_b partial[b][c] in double, fixed order.  All 256 threads take part:
+// thread = (float4 column, row lane); each walks its rows with 4 loads in flight, then the row
+// lanes are folded through shared memory in lane order.  smem needs lanes*W doubles.
+__device__ __forceinline__ void final_combine(const float* partial, int nb, int W, double* sm) {
+  const int W4 = W / 4;                                   // W = 2C is a multiple of 16
+  const int lanes = (BN_THREADS >= W4) ? BN_THREADS / W4 : 1;
+  for (int col0 = 0; col0 < W4; col0 += BN_THREADS) {     // only loops when W4 > 256 (C > 512)
+    const int col = col0 + (int)(threadIdx.x % (lanes > 1 ? W4 : BN_THREADS));
+    const int bl = (lanes > 1) ? (int)(threadIdx.x / W4) : 0;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (col < W4) {
+      const float4* p4 = reinterpret_cast<const float4*>(partial) + col;
+      int b = bl;
+      for (; b + 7 * lanes < nb; b += 8 * lanes) {
+        float4 x[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = __ldcg(partial + (size_t)(b + u) * W + c);
+        for (int u = 0; u < 8; ++u) x[u] = __ldcg(p4 + (size_t)(b + u * lanes) * W4);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += (double)x[u];
+        for (int u = 0; u < 8; ++u) {
+          a0 += (double)x[u].x; a1 += (double)x[u].y; a2 += (double)x[u].z; a3 += (double)x[u].w;
+        }
+      }
+      for (; b < nb; b += lanes) {
+        const float4 x0 = __ldcg(p4 + (size_t)b * W4);
+        a0 += (double)x0.x; a1 += (double)x0.y; a2 += (double)x0.z; a3 += (double)x0.w;
+      }
+      double* dst = sm + (size_t)bl * W + (size_t)col * 4;
+      dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
     }
-    for (; b < nb; ++b) acc[0] += (double)__ldcg(partial + (size_t)b * W + c);
-    out_smem[c] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   }
   __syncthreads();
+  if (lanes > 1) {
+    for (int c = threadIdx.x; c < W; c += BN_THREADS) {
+      double t = sm[c];
+      for (int l = 1; l < lanes; ++l) t += sm[(size_t)l * W + c];
+      sm[c] = t;                                           // row 0 holds the totals
+    }
+    __syncthreads();
+  }
 }
 
 __device__ __forceinline__ bool elect_last_block(unsigned int* ticket) {
@@ -315,8 +337,18 @@ cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s
   const int TPR = p.C / 8;
   if (p.C % 8 != 0 || TPR < 1 || TPR > BN_THREADS || (BN_THREADS % TPR) != 0) return cudaErrorInvalidValue;
   size_t smem = (size_t)(BN_THREADS / TPR) * 2 * p.C * sizeof(float);   // 16 KB staging
-  if (smem < (size_t)2 * p.C * sizeof(double)) smem = (size_t)2 * p.C * sizeof(double);   // final combine
-  const int red_grid = bn_grid(p, bn_partial_rows(sm_count), 8);
+  {   // final combine: lanes * 2C doubles
+    const int W4 = 2 * p.C / 4;
+    const int lanes = (BN_THREADS >= W4) ? BN_THREADS / W4 : 1;
+    const size_t need = (size_t)lanes * 2 * p.C * sizeof(double);
+    if (smem < need) smem = need;
+  }
+  // reductions: few, fat CTAs (8 x 16 B loads in flight per thread) keep the fixed-order combine of
+  // the partial rows short: rows * 2C is bounded by ~32K floats
+  int red_cap = 32768 / (2 * p.C);
+  if (red_cap > bn_partial_rows(sm_count)) red_cap = bn_partial_rows(sm_count);
+  if (red_cap < 16) red_cap = 16;
+  const int red_grid = bn_grid(p, red_cap, 8);
   const int map_grid = bn_grid(p, sm_count * 8, 4);
   switch (which) {
     case 0: bn_fwd_stats_kernel<<<red_grid, BN_THREADS, smem, s>>>(p); break;
