@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--horizon", type=float, default=1.0)
     p.add_argument("--topk", type=float, default=10.0)
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
+                   help="split step: pushes on a side stream overlapping forward/backward")
     p.add_argument("--no-channels-last", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--out", default="")
@@ -86,6 +88,7 @@ def main():
                  dtype=args.dtype, batch_size=gb, batch_mode="global", epochs=10 ** 6,
                  sync_mode="iter" if algo == "decent" else args.sync_mode,
                  horizon=args.horizon, topk_percent=args.topk,
+                 overlap_push=(args.overlap == "on") or (args.overlap == "auto" and N > 1 and backend == "p2p"),
                  channels_last=not args.no_channels_last, cuda_graph=not args.no_graph,
                  train_samples=n_train, test_samples=256, quiet=True, augment=True)
     src = synthetic_source("cifar10", n_train).pin()
@@ -199,7 +202,7 @@ def main():
     events_all = sum_over_ranks(be.num_events(), env)
     dense_msgs = 2 * table.n_tensors * total_steps * N
     push_bytes_step = bytes_rank / max(1, total_steps)
-    kern_per_step = {"decent": 1, "event": 1, "cent": 1, "spevent": 11}[algo]
+    kern_per_step = {"decent": 1, "event": 1, "cent": 1, "spevent": 11}[algo] + (1 if (cfg.overlap_push and algo in ("decent", "event") and N > 1) else 0)
     out = {
         "metric": "images/sec, CIFAR-10 ResNet (reference topology) D-PSGD ring gossip training step",
         "value": value, "unit": "images/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
@@ -210,7 +213,7 @@ def main():
                             if args.model == "resnet18" else args.model,
                    "global_batch": gb, "per_gpu_batch": per_rank, "image": "3x32x32",
                    "parallelism": f"dp{N}-ring-gossip" if algo != "cent" else f"dp{N}-allreduce",
-                   "algorithm": args.algo, "backend": backend, "sync_mode": cfg.sync_mode,
+                   "algorithm": args.algo, "backend": backend, "sync_mode": cfg.sync_mode, "overlap_push": cfg.overlap_push,
                    "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": cfg.cuda_graph,
                    "channels_last": cfg.channels_last,
                    "l2_policy": "per-step working set (theta,grad,mom,2 inboxes = "

@@ -48,6 +48,8 @@ class TrainConfig:
     backend: str = "auto"            # auto | p2p (fused sm_100a kernels) | nccl | gloo
     sync_mode: str = "iter"          # iter (deterministic handshake) | async (reference RMA semantics)
     final_divide_all: bool = True    # reference divides on rank 0 only (Q5)
+    overlap_push: bool = False       # p2p: launch the push half of the step on a side stream so it
+                                     # overlaps forward/backward (False = single fused kernel)
     # ---- data --------------------------------------------------------------
     data: str = "synthetic"          # synthetic | path to dataset root
     sampler: str = "random"          # random | sequential
@@ -137,6 +139,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--initial-comm-passes", type=int, default=None)
     p.add_argument("--backend", default=None, choices=["auto", "p2p", "nccl", "gloo"])
     p.add_argument("--sync-mode", default=None, choices=["iter", "async"])
+    p.add_argument("--overlap-push", action="store_true", default=None)
     p.add_argument("--data", default=None, help="'synthetic' or dataset root directory")
     p.add_argument("--sampler", default=None, choices=["random", "sequential"])
     p.add_argument("--no-augment", dest="augment", action="store_false", default=None)

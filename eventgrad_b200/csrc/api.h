@@ -69,7 +69,11 @@ struct GossipParams {
   uint32_t* ack_from_r;
   uint32_t* ack_to_l;       // peer-mapped
   uint32_t* ack_to_r;
-  unsigned int* ticket;     // last-CTA election
+  uint32_t* pushed_from_l;  // split step: left neighbour has finished ALL its pushes of step k
+  uint32_t* pushed_from_r;
+  uint32_t* pushed_to_l;    // peer-mapped
+  uint32_t* pushed_to_r;
+  unsigned int* ticket;     // [0] last-CTA election (step) [1] push phase
   unsigned int* tensor_done; // [sz] per-tensor count of per-warp partials written this launch
   int* status;              // sticky error word
   unsigned long long timeout_ns;
@@ -85,6 +89,7 @@ struct GossipParams {
   int group_iters;          // tiles per CTA between two flag publications (sync)
   int vec256_push;          // 1: 256-bit peer stores, 0: 2x128-bit
   int need_norm;            // 0: skip norm-on-write + trigger entirely (decent/cent without logs)
+  int phase;                // 0 fused step | 1 push only (side stream, overlaps backward) | 2 wait+mix+SGD
 };
 
 int gossip_max_grid(int device);  // co-resident CTAs (persistent grid upper bound)

@@ -42,11 +42,12 @@ static const std::unordered_map<std::string, Setter<GossipParams>> kGossip = {
     PTRF(GossipParams, tile_ss_l), PTRF(GossipParams, tile_ss_r), PTRF(GossipParams, flag_from_l),
     PTRF(GossipParams, flag_from_r), PTRF(GossipParams, flag_to_l), PTRF(GossipParams, flag_to_r),
     PTRF(GossipParams, ack_from_l), PTRF(GossipParams, ack_from_r), PTRF(GossipParams, ack_to_l),
-    PTRF(GossipParams, ack_to_r), PTRF(GossipParams, ticket), PTRF(GossipParams, tensor_done), PTRF(GossipParams, status),
+    PTRF(GossipParams, ack_to_r), PTRF(GossipParams, pushed_from_l), PTRF(GossipParams, pushed_from_r),
+    PTRF(GossipParams, pushed_to_l), PTRF(GossipParams, pushed_to_r), PTRF(GossipParams, ticket), PTRF(GossipParams, tensor_done), PTRF(GossipParams, status),
     NUMF(GossipParams, timeout_ns), NUMF(GossipParams, lr), NUMF(GossipParams, mu),
     NUMF(GossipParams, do_mix), NUMF(GossipParams, do_push), NUMF(GossipParams, sync),
     NUMF(GossipParams, send_ack), NUMF(GossipParams, zero_grad), NUMF(GossipParams, group_iters),
-    NUMF(GossipParams, vec256_push), NUMF(GossipParams, need_norm), TAB_FIELDS(GossipParams),
+    NUMF(GossipParams, vec256_push), NUMF(GossipParams, need_norm), NUMF(GossipParams, phase), TAB_FIELDS(GossipParams),
     PTRF2(GossipParams, fsm, thres), PTRF2(GossipParams, fsm, last_norm), PTRF2(GossipParams, fsm, last_iter),
     PTRF2(GossipParams, fsm, slopes), PTRF2(GossipParams, fsm, fire), PTRF2(GossipParams, fsm, cur_norm),
     PTRF2(GossipParams, fsm, counters), PTRF2(GossipParams, fsm, pass_num), PTRF2(GossipParams, fsm, log_ring),
@@ -132,6 +133,10 @@ PYBIND11_MODULE(_C, m) {
   m.def("gossip_max_grid", &gossip_max_grid);
   m.def("gossip_step", [](const GossipParams& p, int grid, uintptr_t s) {
     check(launch_gossip_step(p, grid, S(s)), "gossip_step");
+  });
+  m.def("gossip_step_phase", [](GossipParams p, int phase, int grid, uintptr_t s) {
+    p.phase = phase;
+    check(launch_gossip_step(p, grid, S(s)), "gossip_step_phase");
   });
   m.def("gossip_init", [](const GossipParams& p, int grid, int run_fsm, uintptr_t s) {
     check(launch_gossip_init(p, grid, run_fsm, S(s)), "gossip_init");

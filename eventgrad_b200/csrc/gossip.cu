@@ -245,16 +245,62 @@ __device__ __forceinline__ void grid_tail(const GossipParams& p, int step) {
   }
 }
 
+// phase 1 of the split step: push only.  Depends on theta_k and the trigger decisions alone, so
+// it is launched on a side stream at the START of step k and its NVLink traffic hides behind the
+// forward/backward pass.  Publishes ONE "all pushed" flag per neighbour when every CTA is done.
+__device__ __forceinline__ void push_phase(const GossipParams& p, int step) {
+  __shared__ int s_last;
+  const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+  if (p.sync) {
+    if (tid == 0) {   // WAR guard: neighbours have consumed what I pushed at step-1
+      wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
+      wait_ge(p.ack_from_r, (uint32_t)(step - 1), p.status, p.timeout_ns);
+    }
+    __syncthreads();
+  }
+  for (int t = b; t < p.tab.n_tiles; t += G) {
+    if (!p.fsm.fire[p.tab.tile_tensor[t]]) continue;
+    const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+    push_tile(p, base, ld_f8(p.theta + base));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    const unsigned prev = atomicAdd(p.ticket + 1, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    p.ticket[1] = 0u;
+    __threadfence_system();
+    st_release_sys(p.pushed_to_l, (uint32_t)step);
+    st_release_sys(p.pushed_to_r, (uint32_t)step);
+  }
+}
+
 template <bool kMom>
 __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const GossipParams p) {
   const int b = blockIdx.x, G = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int step = *p.fsm.pass_num + 1;
   const int n_tiles = p.tab.n_tiles;
-  const bool push = p.do_push != 0;
+  const bool push = p.do_push != 0 && p.phase != 2;
+
+  if (p.phase == 1) {
+    push_phase(p, step);
+    return;
+  }
+  if (p.phase == 2 && p.sync && p.do_push) {
+    // split step, second half: the neighbours' pushes of this step were issued during my backward
+    if (tid == 0) {
+      wait_ge(p.pushed_from_l, (uint32_t)step, p.status, p.timeout_ns);
+      wait_ge(p.pushed_from_r, (uint32_t)step, p.status, p.timeout_ns);
+    }
+    __syncthreads();
+  }
 
   if (!(p.sync && push)) {
-    // ---------------- async (or no exchange): single pass, theta read once ----------------
+    // ---------------- async / split / no exchange: single pass, theta read once ---------------
     for (int t = b; t < n_tiles; t += G) {
       const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
       const F8 th = ld_f8(p.theta + base);

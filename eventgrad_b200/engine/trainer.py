@@ -86,6 +86,7 @@ class Trainer:
         self.steps_done = 0
         self._graphs = {}
         self._graph_warm = {}
+        self._side = None
         self.train_time_s = 0.0
         if cfg.resume:
             sd = load_checkpoint(cfg.resume, arena=self.arena, backend=self.backend, model=self.model)
@@ -118,6 +119,35 @@ class Trainer:
 
     GRAPH_WARMUP_STEPS = 3
 
+    def _fwd_bwd_launch(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """forward/backward + the backend's kernels, with the theta_k-only half of a split step
+        (neighbour pushes / top-k records) forked onto a side stream so that its NVLink traffic is
+        hidden behind the compute.  Pure enqueue: usable eagerly and under graph capture."""
+        be = self.backend
+        if getattr(be, "overlap", False):
+            cur = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                be.launch_pre()
+            loss = self._fwd_bwd(x, y)
+            cur.wait_stream(self._side)
+            be.launch()
+        else:
+            loss = self._fwd_bwd(x, y)
+            be.launch()
+        return loss
+
+    def _eager_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if getattr(self.backend, "graph_safe", False):
+            loss = self._fwd_bwd_launch(x, y)
+            self.backend.account_step()
+        else:
+            loss = self._fwd_bwd(x, y)
+            self.backend.step()
+        return loss
+
     def _graphed_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """Replay the step from a CUDA graph (per input shape).  The first GRAPH_WARMUP_STEPS steps
         of a shape run eagerly (cuDNN autotune, lazy kernel loading, allocator warm-up); then the
@@ -131,16 +161,15 @@ class Trainer:
             n = self._graph_warm.get(key, 0)
             if n < self.GRAPH_WARMUP_STEPS:
                 self._graph_warm[key] = n + 1
-                loss = self._fwd_bwd(x, y)
-                self.backend.step()
-                return loss
+                return self._eager_step(x, y)
             sx, sy = x.clone(), y.clone()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                sloss = self._fwd_bwd(sx, sy)
                 if whole:
-                    self.backend.launch()
+                    sloss = self._fwd_bwd_launch(sx, sy)
+                else:
+                    sloss = self._fwd_bwd(sx, sy)
             ent = (g, sx, sy, sloss)
             self._graphs[key] = ent
         g, sx, sy, sloss = ent
@@ -160,8 +189,7 @@ class Trainer:
         if self.cfg.cuda_graph and self.device.type == "cuda":
             loss = self._graphed_step(x, y)
         else:
-            loss = self._fwd_bwd(x, y)
-            self.backend.step()
+            loss = self._eager_step(x, y)
         self.steps_done += 1
         self.last_loss = loss
         return loss

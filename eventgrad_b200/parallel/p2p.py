@@ -49,6 +49,8 @@ def build_layout(table: TensorTable, cfg, world: int, max_grid: int) -> Layout:
     lay.add("flag_from_r", nflag)
     lay.add("ack_from_l", 256)
     lay.add("ack_from_r", 256)
+    lay.add("pushed_from_l", 256)
+    lay.add("pushed_from_r", 256)
     lay.add("ar_flags", 3 * max_grid * world * 4)
     return lay
 
@@ -73,7 +75,7 @@ class P2PBackend(CommBackend):
 
     def __init__(self, cfg, arena: ParamArena, ring, env, group=None, symm=None,
                  grid_cap: int = 0, defer_connect: bool = False, group_iters: int = 4,
-                 timeout_ns: int = DEFAULT_TIMEOUT_NS, vec256_push: bool = True):
+                 timeout_ns: int = DEFAULT_TIMEOUT_NS, vec256_push: bool = True, push_grid: int = 0):
         super().__init__(cfg, arena, ring)
         from ..ops import ext
         self.C = ext()
@@ -94,6 +96,10 @@ class P2PBackend(CommBackend):
         self.gossip = cfg.algo in ("decent", "event", "spevent")
         self.sparse = cfg.algo == "spevent"
         self.do_comm = self.comm_enabled and self.gossip
+        # split step: everything that depends only on theta_k (pushes / top-k records) is launched on a
+        # side stream at the start of the step and overlaps forward+backward
+        self.overlap = bool(getattr(cfg, "overlap_push", False)) and self.do_comm
+        self.push_grid = push_grid
         self.recv_rms = cfg.dataset == "mnist"
         dev = self.dev
         i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=dev)
@@ -123,7 +129,7 @@ class P2PBackend(CommBackend):
         self.cur_norm = zf(t.n_tensors)
         self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
         self.d_pass = zi(1)
-        self.ticket = zi(4)
+        self.ticket = zi(8)      # [0] step tail, [1] push phase, [4] sparse, [6] all-reduce
         self.status = zi(1)
         self.tile_ss = zf(t.n_tiles * 8)
         self.tensor_done = zi(t.n_tensors)
@@ -195,6 +201,9 @@ class P2PBackend(CommBackend):
                 "flag_to_l": win.addr("flag_from_r", L), "flag_to_r": win.addr("flag_from_l", R),
                 "ack_from_l": win.addr("ack_from_l"), "ack_from_r": win.addr("ack_from_r"),
                 "ack_to_l": win.addr("ack_from_r", L), "ack_to_r": win.addr("ack_from_l", R),
+                "pushed_from_l": win.addr("pushed_from_l"), "pushed_from_r": win.addr("pushed_from_r"),
+                "pushed_to_l": win.addr("pushed_from_r", L), "pushed_to_r": win.addr("pushed_from_l", R),
+                "phase": 0,
                 "fsm.thres": P(self.thres), "fsm.last_norm": P(self.last_norm),
                 "fsm.last_iter": P(self.last_iter), "fsm.slopes": P(self.slopes),
                 "fsm.fire": P(self.fire), "fsm.cur_norm": P(self.cur_norm),
@@ -228,7 +237,7 @@ class P2PBackend(CommBackend):
                 "t_k": P(self.d_k), "t_rec_off": P(self.d_rec_off), "hist": P(self.hist),
                 "sel_prefix": P(self.sel_prefix), "sel_remain": P(self.sel_remain),
                 "tile_gt": P(self.tile_gt), "tile_eq": P(self.tile_eq), "t_gt_total": P(self.t_gt_total),
-                "fire": P(self.fire), "pass_num": P(self.d_pass), "ticket": P(self.ticket[1:]),
+                "fire": P(self.fire), "pass_num": P(self.d_pass), "ticket": P(self.ticket[4:]),
                 "status": P(self.status), "timeout_ns": int(self.timeout_ns), "sync": 1 if self.sync else 0,
             })
             self.sp = sp
@@ -238,7 +247,7 @@ class P2PBackend(CommBackend):
         self.d_peer_theta = torch.tensor([win.addr("theta", r) for r in range(W)], dtype=torch.int64, device=self.dev)
         self.d_peer_flags = torch.tensor([win.addr("ar_flags", r) for r in range(W)], dtype=torch.int64, device=self.dev)
         common = {"peer_flags": P(self.d_peer_flags), "flags": win.addr("ar_flags"),
-                  "ticket": P(self.ticket[2:]), "status": P(self.status), "step_ctr": P(self.ar_ctr),
+                  "ticket": P(self.ticket[6:]), "status": P(self.status), "step_ctr": P(self.ar_ctr),
                   "timeout_ns": int(self.timeout_ns), "n_tiles": t.n_tiles, "rank": self.ring.rank,
                   "world": W, "lr": float(cfg.lr), "mu": float(cfg.momentum)}
         ap = C.AllReduceParams()
@@ -267,6 +276,19 @@ class P2PBackend(CommBackend):
     # ------------------------------------------------------------------ step
     graph_safe = True      # launch() only enqueues kernels whose per-step state lives on the device
 
+    def launch_pre(self) -> None:
+        """Split step, first half (side stream, concurrent with forward/backward): push theta_k to
+        the neighbours / select + push the top-k records.  Depends only on theta_k and fire[]."""
+        if not self.overlap:
+            return
+        C, s = self.C, self._stream()
+        with torch.cuda.device(self.dev):
+            if self.sparse:
+                C.sparse_select_push(self.sp, self.grid, s)
+            else:
+                g = self.push_grid or max(1, min(self.grid, 128))
+                C.gossip_step_phase(self.gp, 1, g, s)
+
     def launch(self) -> None:
         """Enqueue this step's kernels on the current stream (CUDA-graph capturable: the step
         counter, trigger state and handshake sequence numbers are all device resident)."""
@@ -279,9 +301,14 @@ class P2PBackend(CommBackend):
                     C.gossip_step(self.gp, self.grid, s)       # plain fused SGD
                 return
             if self.sparse and self.do_comm:
-                C.sparse_select_push(self.sp, self.grid, s)
+                if not self.overlap:
+                    C.sparse_select_push(self.sp, self.grid, s)
                 C.sparse_apply(self.sp, self.grid, s)
-            C.gossip_step(self.gp, self.grid, s)
+                C.gossip_step(self.gp, self.grid, s)
+            elif self.overlap:
+                C.gossip_step_phase(self.gp, 2, self.grid, s)
+            else:
+                C.gossip_step(self.gp, self.grid, s)
 
     def account_step(self) -> None:
         """Host-side bookkeeping of one executed step (after launch() or a graph replay)."""
@@ -292,6 +319,8 @@ class P2PBackend(CommBackend):
             self.host_bytes += 2 * self.table.n_elems * 4
 
     def step(self) -> None:
+        if self.overlap:        # no compute to hide behind when called stand-alone: run both halves in order
+            self.launch_pre()
         self.launch()
         self.account_step()
 
@@ -382,7 +411,7 @@ class P2PBackend(CommBackend):
         torch.cuda.synchronize(self.dev)
 
     def _reset_handshake(self, step: int) -> None:
-        for name in ("flag_from_l", "flag_from_r", "ack_from_l", "ack_from_r"):
+        for name in ("flag_from_l", "flag_from_r", "ack_from_l", "ack_from_r", "pushed_from_l", "pushed_from_r"):
             self.win.view(name, torch.int32).fill_(step)
         if self.sparse:
             for name in ("done_from_l", "done_from_r"):

@@ -35,13 +35,14 @@ def main():
     ap.add_argument("--topk", type=float, default=10.0)
     ap.add_argument("--warm", type=int, default=4)
     ap.add_argument("--sync-mode", default="iter")
+    ap.add_argument("--overlap", action="store_true")
     a = ap.parse_args()
     dev_pref = "cpu" if a.backend == "gloo" else "cuda"
     env = init_distributed(dev_pref)
     cfg = TrainConfig(algo=a.algo, dataset=a.dataset, model=a.model, lr=0.05, momentum=a.momentum,
                       horizon=a.horizon, thres_type=a.thres_type, constant=a.constant,
                       topk_percent=a.topk, initial_comm_passes=a.warm, backend=a.backend,
-                      sync_mode=a.sync_mode).validate()
+                      sync_mode=a.sync_mode, overlap_push=a.overlap).validate()
     torch.manual_seed(0)
     model = build_model(a.model)
     ring = Ring(env.rank, env.world)
@@ -107,8 +108,8 @@ def main():
                 # reference RMA semantics: neighbours' values may be one step stale or newer, so the
                 # trajectory is timing dependent -- only sanity is checked (finite, near the oracle)
                 same = bool(torch.isfinite(got).all()) and float((got - sim.theta[r]).abs().max()) < 0.5
-            elif a.algo != "cent":
-                same = torch.equal(got, sim.theta[r])
+            elif a.algo != "cent" and a.backend != "nccl":
+                same = torch.equal(got, sim.theta[r])       # (CUDA eager div_(3) multiplies by 1/3: nccl is ~1 ulp off)
             else:
                 same = torch.allclose(got, sim.theta[r], rtol=1e-5, atol=1e-6)
             if not same:

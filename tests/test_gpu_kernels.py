@@ -263,3 +263,27 @@ def test_decode_augment_kernel(nhwc, bf16):
         assert out.is_contiguous(memory_format=torch.channels_last)
     out2 = decode_augment(x, 1.0, 0.0, 1.0, None)
     assert torch.equal(out2, x.float())
+
+
+@pytest.mark.parametrize("algo", ["decent", "event", "spevent"])
+@pytest.mark.parametrize("R", [2, 3])
+def test_split_step_overlap_mode_matches_simulator(algo, R):
+    """overlap_push: push half (side stream in the trainer) + wait/mix half == the fused kernel."""
+    cfg = _cfg(algo, overlap_push=True, initial_comm_passes=4, horizon=1.0)
+    w = _world(cfg, R)
+    assert all(be.overlap for be in w.backends)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, algo, TriggerConfig.from_train(cfg), lr=cfg.lr,
+                        momentum=cfg.momentum, topk_percent=cfg.topk_percent, serial_skip=False)
+    for s in range(10):
+        fires = [be.fire.clone().bool() for be in w.backends] if algo != "decent" else None
+        g = _mask_pad(w, _grads(R, t.n_padded, 321 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g], fires=fires)
+    torch.cuda.synchronize()
+    for r, be in enumerate(w.backends):
+        be.check_status()
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r}"
+        if algo != "decent":
+            assert be.num_events() == sim.events[r]
+    w.close()

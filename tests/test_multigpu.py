@@ -34,6 +34,12 @@ def test_p2p_vs_simulator(algo):
         _run(w, "--algo", algo, "--backend", "p2p", "--steps", "12")
 
 
+@pytest.mark.parametrize("algo", ["decent", "event", "spevent"])
+def test_p2p_overlap_vs_simulator(algo):
+    for w in _worlds():
+        _run(w, "--algo", algo, "--backend", "p2p", "--steps", "10", "--overlap")
+
+
 def test_p2p_event_async():
     for w in _worlds()[:1]:
         _run(w, "--algo", "event", "--backend", "p2p", "--sync-mode", "async", "--thres-type", "0",
