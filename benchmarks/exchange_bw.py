@@ -66,7 +66,7 @@ def main():
 
     # ---- dense fused gossip (decent) -----------------------------------------------------------
     for name, kw in (("v256", dict(vec256_push=True)), ("v128", dict(vec256_push=False)),
-                     ("q1", dict(group_iters=1)), ("q16", dict(group_iters=16))):
+                     ("d1", dict(group_iters=1)), ("d4", dict(group_iters=4))):
         cfg = TrainConfig(algo="decent", sync_mode="iter", **base).validate()
         arena, be = make(cfg, env, a.model, **kw)
         n_bytes = arena.table.n_elems * 4
@@ -78,6 +78,20 @@ def main():
         be.close()
         del arena, be
         torch.cuda.empty_cache()
+
+    # ---- push-only kernel (phase 1): the ceiling of SM-issued NVLink stores, vs grid size ----------
+    cfg = TrainConfig(algo="decent", sync_mode="iter", overlap_push=True, **base).validate()
+    arena, be = make(cfg, env, a.model)
+    n_bytes = arena.table.n_elems * 4
+    for g in (32, 64, 128, 296, 592):
+        def both():
+            be.C.gossip_step_phase(be.gp, 1, g, be._stream())
+            be.C.gossip_step_phase(be.gp, 2, be.grid, be._stream())
+        ms_both = timed(both, env, a.iters)
+        res[f"push_only_grid{g}"] = {"ms_push_plus_mix": ms_both}
+    ms_mix = None
+    be.check_status()
+    be.close(); del arena, be; torch.cuda.empty_cache()
 
     # ---- async dense (no handshake) and event at ~0 fire fraction -------------------------------
     cfg = TrainConfig(algo="event", sync_mode="async", thres_type=0, constant=0.0, **base).validate()

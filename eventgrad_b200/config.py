@@ -48,6 +48,8 @@ class TrainConfig:
     backend: str = "auto"            # auto | p2p (fused sm_100a kernels) | nccl | gloo
     sync_mode: str = "iter"          # iter (deterministic handshake) | async (reference RMA semantics)
     final_divide_all: bool = True    # reference divides on rank 0 only (Q5)
+    grad_table: bool = True          # p2p gossip: step kernel reads autograd's gradients in place (+ bf16
+                                     # shadow weights under dtype=bf16) instead of an fp32 grad arena
     overlap_push: bool = False       # p2p: launch the push half of the step on a side stream so it
                                      # overlaps forward/backward (False = single fused kernel)
     # ---- data --------------------------------------------------------------
@@ -140,6 +142,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--backend", default=None, choices=["auto", "p2p", "nccl", "gloo"])
     p.add_argument("--sync-mode", default=None, choices=["iter", "async"])
     p.add_argument("--overlap-push", action="store_true", default=None)
+    p.add_argument("--no-grad-table", dest="grad_table", action="store_false", default=None)
     p.add_argument("--data", default=None, help="'synthetic' or dataset root directory")
     p.add_argument("--sampler", default=None, choices=["random", "sequential"])
     p.add_argument("--no-augment", dest="augment", action="store_false", default=None)

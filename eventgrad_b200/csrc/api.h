@@ -57,11 +57,13 @@ struct GossipParams {
   float* push_l;            // peer-mapped: LEFT neighbour's inbox_r
   float* push_r;            // peer-mapped: RIGHT neighbour's inbox_l
   __nv_bfloat16* shadow;    // optional bf16 copy of theta_{k+1} for the next forward
+  const void* const* t_grad_ptr;  // optional [sz]: read each tensor's gradient in place (table mode)
+  const int* t_grad_bf16;         // [sz] 1: that gradient is bf16, 0: fp32
   float* tile_ss;           // [n_tiles * 8] per-warp sum theta_{k+1}^2
   float* tile_ss_l;         // optional (logging): sum inbox_l^2
   float* tile_ss_r;
   // iter-sync handshake (all monotonic step counters)
-  uint32_t* flag_from_l;    // local, written by left neighbour   [n_groups * grid]
+  uint32_t* flag_from_l;    // local, written by left neighbour   [n_tiles * 8] (tile, warp)
   uint32_t* flag_from_r;
   uint32_t* flag_to_l;      // peer-mapped: left neighbour's flag_from_r
   uint32_t* flag_to_r;      // peer-mapped: right neighbour's flag_from_l
@@ -86,7 +88,7 @@ struct GossipParams {
   int sync;                 // 1: iter-sync handshake, 0: async (reference RMA semantics)
   int send_ack;             // sync: write acks in the tail (0 when another kernel acks)
   int zero_grad;
-  int group_iters;          // tiles per CTA between two flag publications (sync)
+  int group_iters;          // iter-sync software-pipeline depth in tiles (push j, mix j-D)
   int vec256_push;          // 1: 256-bit peer stores, 0: 2x128-bit
   int need_norm;            // 0: skip norm-on-write + trigger entirely (decent/cent without logs)
   int phase;                // 0 fused step | 1 push only (side stream, overlaps backward) | 2 wait+mix+SGD

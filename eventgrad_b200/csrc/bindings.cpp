@@ -38,7 +38,8 @@ using Setter = std::function<void(S&, py::object)>;
 static const std::unordered_map<std::string, Setter<GossipParams>> kGossip = {
     PTRF(GossipParams, theta), PTRF(GossipParams, grad), PTRF(GossipParams, mom),
     PTRF(GossipParams, inbox_l), PTRF(GossipParams, inbox_r), PTRF(GossipParams, push_l),
-    PTRF(GossipParams, push_r), PTRF(GossipParams, shadow), PTRF(GossipParams, tile_ss),
+    PTRF(GossipParams, push_r), PTRF(GossipParams, shadow), PTRF(GossipParams, t_grad_ptr),
+    PTRF(GossipParams, t_grad_bf16), PTRF(GossipParams, tile_ss),
     PTRF(GossipParams, tile_ss_l), PTRF(GossipParams, tile_ss_r), PTRF(GossipParams, flag_from_l),
     PTRF(GossipParams, flag_from_r), PTRF(GossipParams, flag_to_l), PTRF(GossipParams, flag_to_r),
     PTRF(GossipParams, ack_from_l), PTRF(GossipParams, ack_from_r), PTRF(GossipParams, ack_to_l),

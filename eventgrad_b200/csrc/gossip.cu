@@ -7,8 +7,8 @@
 //               (peer-mapped pointers -> NVLink 5 / NVSwitch).  Below threshold nothing is
 //               stored, so link bytes scale with events (MPI_Put semantics,
 //               /root/reference/dcifar10/event/event.cpp:317-332).
-//   2. sync   : iter mode publishes one release-flag per (CTA, tile group) and waits for the
-//               two neighbours' matching flags, so exchange and math overlap group by group;
+//   2. sync   : iter mode publishes one release-flag per (tile, warp) and waits for the two
+//               neighbours' matching flags, so exchange and math overlap slice by slice;
 //               async mode reads whatever the inboxes hold (reference: unsynchronised window
 //               reads, event.cpp:372-374).
 //   3. mix+opt: theta <- ((theta+L)+R)/3 ; m <- mu*m+g ; theta <- theta - lr*m   (event.cpp:
@@ -157,6 +157,44 @@ __device__ __forceinline__ void push_tile(const GossipParams& p, size_t base, co
   }
 }
 
+// Gradient of this thread's 8 elements.  Flat mode: the fp32 grad arena.  Table mode: autograd's
+// own gradient tensors are read in place through a per-tensor pointer table (bf16 or fp32, exactly
+// numel elements each) -- no AccumulateGrad kernels, no grad arena traffic, no zeroing.
+__device__ __forceinline__ F8 load_grad(const GossipParams& p, int t, size_t base, int tid) {
+  if (p.t_grad_ptr == nullptr) return ld_f8(p.grad + base);
+  const int i = p.tab.tile_tensor[t];
+  const int off = (t - p.tab.t_tile_start[i]) * EG_TILE + tid * EG_VEC;
+  const int numel = p.tab.t_numel[i];
+  F8 g;
+  if (p.t_grad_bf16[i]) {
+    const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.t_grad_ptr[i]);
+    if (off + EG_VEC <= numel) {
+      const uint4 u = *reinterpret_cast<const uint4*>(gp + off);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        g.v[2 * e] = f.x;
+        g.v[2 * e + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g.v[e] = (off + e < numel) ? __bfloat162float(gp[off + e]) : 0.f;
+    }
+  } else {
+    const float* gp = reinterpret_cast<const float*>(p.t_grad_ptr[i]);
+    if (off + EG_VEC <= numel) {
+      const float4 a = *reinterpret_cast<const float4*>(gp + off), b = *reinterpret_cast<const float4*>(gp + off + 4);
+      g.v[0] = a.x; g.v[1] = a.y; g.v[2] = a.z; g.v[3] = a.w;
+      g.v[4] = b.x; g.v[5] = b.y; g.v[6] = b.z; g.v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g.v[e] = (off + e < numel) ? gp[off + e] : 0.f;
+    }
+  }
+  return g;
+}
+
 // mix + SGD + norm-on-write for one tile. `th` already holds theta_k for this thread's 8 floats.
 template <bool kMom>
 __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t base, F8 th, int lane,
@@ -169,7 +207,7 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
     L = ld_f8_cg(p.inbox_l + base);
     R = ld_f8_cg(p.inbox_r + base);
   }
-  const F8 g = ld_f8(p.grad + base);
+  const F8 g = load_grad(p, t, base, threadIdx.x);
   if (kMom) m = ld_f8(p.mom + base);
   if (p.do_mix) {
 #pragma unroll
@@ -199,7 +237,7 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
   }
   st_f8(p.theta + base, th);
   if (p.shadow != nullptr) st_bf16x8(p.shadow + base, th);
-  if (p.zero_grad) {
+  if (p.zero_grad && p.t_grad_ptr == nullptr) {
     F8 z;
 #pragma unroll
     for (int e = 0; e < 8; ++e) z.v[e] = 0.f;
@@ -308,7 +346,12 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
       mix_tile<kMom>(p, t, base, th, lane, warp, step);
     }
   } else {
-    // ---------------- iter-sync: software-pipelined push(q) | wait+mix(q-1) -----------------
+    // ---------------- iter-sync: per-WARP software pipeline, no block barriers ------------------
+    // Every warp owns 256 floats of each of its CTA's tiles.  It pushes its slice of tile j and
+    // publishes a release-flag (tile, warp) to both neighbours, then consumes tile j-D: waits for the
+    // neighbours' flags of that slice (normally long set -- the ring is symmetric) and mixes it.
+    // Warps never wait for each other, so flag latency and the sys-scope fence of one warp hide
+    // behind the streaming of the other 31 warps on the SM.
     __shared__ int s_ok;
     if (tid == 0) {
       // WAR guard: neighbours must have consumed what I pushed at step-1 before I overwrite it
@@ -317,39 +360,32 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
       s_ok = ok;
     }
     __syncthreads();
-    const int Q = p.group_iters;
-    const int iters = (n_tiles + G - 1) / G;      // same on every CTA and every rank
-    const int n_groups = (iters + Q - 1) / Q;
-    for (int q = 0; q <= n_groups; ++q) {
-      if (q < n_groups) {
-        for (int j = q * Q; j < min(iters, (q + 1) * Q); ++j) {
-          const int t = b + j * G;
-          if (t < n_tiles && p.fsm.fire[p.tab.tile_tensor[t]]) {
-            const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
-            push_tile(p, base, ld_f8(p.theta + base));
-          }
+    const int D = p.group_iters;                   // pipeline depth in tiles
+    const int iters = (n_tiles + G - 1) / G;
+    for (int j = 0; j < iters + D; ++j) {
+      const int t = b + j * G;
+      if (j < iters && t < n_tiles) {
+        const bool fired = p.fsm.fire[p.tab.tile_tensor[t]] != 0;
+        if (fired) {
+          const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+          push_tile(p, base, ld_f8(p.theta + base));
         }
-        __syncthreads();   // all of this CTA's stores for group q are issued
-        if (tid == 0) {
-          fence_sys();     // ... and performed at system scope before the flags
-          st_release_sys(p.flag_to_l + (size_t)q * G + b, (uint32_t)step);
-          st_release_sys(p.flag_to_r + (size_t)q * G + b, (uint32_t)step);
+        __syncwarp();
+        if (lane == 0) {
+          if (fired) fence_sys();                  // my warp's stores are performed before the flag
+          st_release_sys(p.flag_to_l + (size_t)t * EG_WARPS + warp, (uint32_t)step);
+          st_release_sys(p.flag_to_r + (size_t)t * EG_WARPS + warp, (uint32_t)step);
         }
       }
-      if (q > 0) {
-        const int c = q - 1;
-        if (tid == 0) {
-          wait_ge(p.flag_from_l + (size_t)c * G + b, (uint32_t)step, p.status, p.timeout_ns);
-          wait_ge(p.flag_from_r + (size_t)c * G + b, (uint32_t)step, p.status, p.timeout_ns);
+      const int t2 = b + (j - D) * G;
+      if (j >= D && t2 < n_tiles) {
+        if (lane == 0) {
+          wait_ge(p.flag_from_l + (size_t)t2 * EG_WARPS + warp, (uint32_t)step, p.status, p.timeout_ns);
+          wait_ge(p.flag_from_r + (size_t)t2 * EG_WARPS + warp, (uint32_t)step, p.status, p.timeout_ns);
         }
-        __syncthreads();
-        for (int j = c * Q; j < min(iters, (c + 1) * Q); ++j) {
-          const int t = b + j * G;
-          if (t < n_tiles) {
-            const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
-            mix_tile<kMom>(p, t, base, ld_f8(p.theta + base), lane, warp, step);
-          }
-        }
+        __syncwarp();
+        const size_t base = (size_t)t2 * EG_TILE + (size_t)tid * EG_VEC;
+        mix_tile<kMom>(p, t2, base, ld_f8(p.theta + base), lane, warp, step);
       }
     }
   }

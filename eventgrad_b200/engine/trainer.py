@@ -63,6 +63,8 @@ class Trainer:
             theta_buf, grad_buf, self._symm = preallocate_arena_buffers(self.model, cfg, env, group)
         self.arena = ParamArena(self.model, dev, theta=theta_buf, grad=grad_buf,
                                 with_momentum=True, channels_last=cfg.channels_last and dev.type == "cuda")
+        if want_p2p and cfg.grad_table and cfg.algo != "cent":
+            self.arena.enable_table_mode(shadow=(cfg.dtype == "bf16"))
         if cfg.channels_last and dev.type == "cuda":
             pass  # activations are produced NHWC by the loader; conv weights already NHWC views
         self.backend = make_backend(cfg, self.arena, self.ring, env, group) if not want_p2p else \
@@ -87,6 +89,7 @@ class Trainer:
         self._graphs = {}
         self._graph_warm = {}
         self._side = None
+        self._graph_keepalive = []
         self.train_time_s = 0.0
         if cfg.resume:
             sd = load_checkpoint(cfg.resume, arena=self.arena, backend=self.backend, model=self.model)
@@ -112,6 +115,8 @@ class Trainer:
         with self._autocast():
             out = self.model(x)
         loss = F.cross_entropy(out.float(), y)     # == nll_loss(log_softmax(.)) (event.cpp:268,:291)
+        if self.arena.table_mode:
+            self.arena.clear_compute_grads()       # fresh gradient tensors, consumed in place by the step kernel
         loss.backward()
         with torch.no_grad():
             self.correct += (out.argmax(1) == y).sum()
@@ -133,10 +138,13 @@ class Trainer:
                 be.launch_pre()
             loss = self._fwd_bwd(x, y)
             cur.wait_stream(self._side)
-            be.launch()
         else:
             loss = self._fwd_bwd(x, y)
-            be.launch()
+        if self.arena.table_mode:
+            keep = be.update_grad_table(self.arena.compute, persistent=torch.cuda.is_current_stream_capturing())
+            if torch.cuda.is_current_stream_capturing():
+                self._graph_keepalive.append(keep)
+        be.launch()
         return loss
 
     def _eager_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -13,15 +13,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.shadow import ShadowConv2d, ShadowLinear
+
 
 class _MnistCNN(nn.Module):
     def __init__(self, k: int, flat: int, hidden: int):
         super().__init__()
-        self.conv1 = nn.Conv2d(1, 10, k)
-        self.conv2 = nn.Conv2d(10, 20, k)
+        self.conv1 = ShadowConv2d(1, 10, k)
+        self.conv2 = ShadowConv2d(10, 20, k)
         self.conv2_drop = nn.Dropout2d()
-        self.fc1 = nn.Linear(flat, hidden)
-        self.fc2 = nn.Linear(hidden, 10)
+        self.fc1 = ShadowLinear(flat, hidden)
+        self.fc2 = ShadowLinear(hidden, 10)
         self._flat = flat
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -9,16 +9,18 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.shadow import ShadowConv2d, ShadowLinear
+
 
 class LeNetCifar(nn.Module):
     def __init__(self, classes: int = 10):
         super().__init__()
-        self.conv1 = nn.Conv2d(3, 6, 5)
-        self.conv2 = nn.Conv2d(6, 16, 5)
+        self.conv1 = ShadowConv2d(3, 6, 5)
+        self.conv2 = ShadowConv2d(6, 16, 5)
         self.conv2_drop = nn.Dropout2d()
-        self.fc1 = nn.Linear(16 * 5 * 5, 120)
-        self.fc2 = nn.Linear(120, 84)
-        self.fc3 = nn.Linear(84, classes)
+        self.fc1 = ShadowLinear(16 * 5 * 5, 120)
+        self.fc2 = ShadowLinear(120, 84)
+        self.fc3 = ShadowLinear(84, classes)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = F.max_pool2d(F.relu(self.conv1(x)), 2)

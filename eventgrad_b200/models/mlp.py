@@ -10,13 +10,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.shadow import ShadowConv2d, ShadowLinear
+
 
 class MLP(nn.Module):
     def __init__(self, in_features: int = 784, hidden: int = 128, classes: int = 10,
                  relu_logits: bool = True):
         super().__init__()
-        self.fc1 = nn.Linear(in_features, hidden)
-        self.fc2 = nn.Linear(hidden, classes)
+        self.fc1 = ShadowLinear(in_features, hidden)
+        self.fc2 = ShadowLinear(hidden, classes)
         self.relu_logits = relu_logits
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

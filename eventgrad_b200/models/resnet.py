@@ -24,10 +24,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..ops.bn_act import FusedBNAct
+from ..ops.shadow import ShadowConv2d, ShadowLinear
 
 
 def conv_op(cin: int, cout: int, k: int, stride: int, padding: int) -> nn.Conv2d:
-    return nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
+    return ShadowConv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
 
 
 class BasicBlock(nn.Module):
@@ -81,7 +82,7 @@ class ResNet(nn.Module):
         self.layer2 = self._make_layer(block, 128, layers[1], 2)
         self.layer3 = self._make_layer(block, 256, layers[2], 2)
         self.layer4 = self._make_layer(block, 512, layers[3], 2)
-        self.fc = nn.Linear(512 * block.expansion, classes)
+        self.fc = ShadowLinear(512 * block.expansion, classes)
 
     def _make_layer(self, block, cout: int, blocks: int, stride: int) -> nn.Sequential:
         downsample = None

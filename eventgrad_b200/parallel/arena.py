@@ -100,6 +100,9 @@ class ParamArena:
         self.grad = _buf(grad)
         self.mom = torch.zeros(n, dtype=torch.float32, device=self.device) if with_momentum else None
         self.params: List[nn.Parameter] = []
+        self.table_mode = False
+        self.compute: List[torch.Tensor] = []
+        self.shadow: Optional[torch.Tensor] = None
         with torch.no_grad():
             for i, (_, p) in enumerate(named):
                 v = self.view(self.theta, i)
@@ -110,6 +113,37 @@ class ParamArena:
         # BN running stats etc. stay outside the arena (never exchanged: SURVEY.md Q6)
         for b in model.buffers():
             b.data = b.data.to(self.device)
+
+    # ------------------------------------------------------------------
+    def enable_table_mode(self, shadow: bool) -> None:
+        """Gradient-table mode of the fused step kernel: autograd's gradient tensors are read in
+        place, so parameters carry NO pre-set .grad.  With `shadow`, Conv/Linear weights additionally
+        get a bf16 leaf copy (view of self.shadow, same physical layout as the master) that the
+        forward pass uses; `compute[i]` is the leaf whose .grad belongs to arena tensor i."""
+        from ..ops.shadow import ShadowConv2d, ShadowLinear
+        self.table_mode = True
+        self.compute = list(self.params)
+        self.shadow = None
+        for p in self.params:
+            p.grad = None
+        if shadow:
+            self.shadow = torch.zeros(self.table.n_padded, dtype=torch.bfloat16, device=self.device)
+            idx = {id(p): i for i, p in enumerate(self.params)}
+            for m in self.model.modules():
+                if isinstance(m, (ShadowConv2d, ShadowLinear)):
+                    i = idx[id(m.weight)]
+                    m.w16 = self.view(self.shadow, i).requires_grad_(True)
+                    self.compute[i] = m.w16
+                    self.params[i].requires_grad_(False)
+                    if m.bias is not None:
+                        j = idx[id(m.bias)]
+                        m.b16 = self.view(self.shadow, j).requires_grad_(True)
+                        self.compute[j] = m.b16
+                        self.params[j].requires_grad_(False)
+
+    def clear_compute_grads(self) -> None:
+        for c in self.compute:
+            c.grad = None
 
     # ------------------------------------------------------------------
     def view(self, buf: torch.Tensor, i: int) -> torch.Tensor:

@@ -44,7 +44,7 @@ def build_layout(table: TensorTable, cfg, world: int, max_grid: int) -> Layout:
         lay.add("seq_from_r", table.n_tensors * 4)
         lay.add("done_from_l", 256)
         lay.add("done_from_r", 256)
-    nflag = (table.n_tiles + 2 * max_grid) * 4
+    nflag = (table.n_tiles * 8 + 64) * 4      # one flag per (tile, warp)
     lay.add("flag_from_l", nflag)
     lay.add("flag_from_r", nflag)
     lay.add("ack_from_l", 256)
@@ -74,7 +74,7 @@ class P2PBackend(CommBackend):
     zeroes_grad = True     # the fused kernels clear grad after consuming it
 
     def __init__(self, cfg, arena: ParamArena, ring, env, group=None, symm=None,
-                 grid_cap: int = 0, defer_connect: bool = False, group_iters: int = 4,
+                 grid_cap: int = 0, defer_connect: bool = False, group_iters: int = 2,
                  timeout_ns: int = DEFAULT_TIMEOUT_NS, vec256_push: bool = True, push_grid: int = 0):
         super().__init__(cfg, arena, ring)
         from ..ops import ext
@@ -153,6 +153,13 @@ class P2PBackend(CommBackend):
             self.tile_gt, self.tile_eq, self.t_gt_total = zi(t.n_tiles), zi(t.n_tiles), zi(t.n_tensors)
             self.applied_l, self.applied_r = zi(t.n_tensors), zi(t.n_tensors)
         self.ar_ctr = zi(1)
+        # gradient pointer table (table mode): device arrays + rotating pinned staging
+        self.table_mode = bool(getattr(arena, "table_mode", False)) and cfg.algo != "cent"
+        self.d_gptr = torch.zeros(t.n_tensors, dtype=torch.int64, device=dev)
+        self.d_gbf16 = zi(t.n_tensors)
+        self._stage = []
+        self._stage_i = 0
+        self._grads_alive = None
         self.host_bytes = 0
         self._connected = False
         self.gp = self.ap = self.ap_avg = self.sp = None
@@ -187,6 +194,9 @@ class P2PBackend(CommBackend):
             gp.update({
                 "theta": P(a.theta), "grad": P(a.grad), "mom": P(a.mom) if cfg.momentum != 0 else 0,
                 "tile_ss": P(self.tile_ss), "tile_ss_l": P(self.tile_ss_l), "tile_ss_r": P(self.tile_ss_r),
+                "shadow": P(getattr(a, "shadow", None)) if self.table_mode else 0,
+                "t_grad_ptr": P(self.d_gptr) if self.table_mode else 0,
+                "t_grad_bf16": P(self.d_gbf16) if self.table_mode else 0,
                 "ticket": P(self.ticket), "tensor_done": P(self.tensor_done), "status": P(self.status),
                 "timeout_ns": int(self.timeout_ns),
                 "lr": float(cfg.lr), "mu": float(cfg.momentum),
@@ -262,8 +272,8 @@ class P2PBackend(CommBackend):
                    "two_shot": 1})
         self.ap_avg = av
         self._connected = True
-        if self.gossip:
-            self._init_norms(run_fsm=True)
+        if self.gossip or self.table_mode:
+            self._init_norms(run_fsm=self.gossip)
         boot.barrier()
 
     def _stream(self) -> int:
@@ -272,6 +282,45 @@ class P2PBackend(CommBackend):
     def _init_norms(self, run_fsm: bool) -> None:
         with torch.cuda.device(self.dev):
             self.C.gossip_init(self.gp, self.grid, 1 if run_fsm else 0, self._stream())
+
+    # ------------------------------------------------------------------ gradient table
+    def update_grad_table(self, compute, persistent: bool = False):
+        """Point the step kernel at this backward's gradient tensors (one pointer + dtype flag per
+        arena tensor).  Eager mode: every step, through rotating pinned staging buffers.  Graph
+        capture: once -- the captured backward writes its gradients to fixed addresses; pass
+        persistent=True and keep the returned staging buffers alive with the graph."""
+        if not self.table_mode:
+            return None
+        n = self.table.n_tensors
+        if persistent:
+            hp, hf = torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory()
+            ev = None
+        else:
+            if len(self._stage) < 4:
+                self._stage.append((torch.empty(n, dtype=torch.int64).pin_memory(),
+                                    torch.empty(n, dtype=torch.int32).pin_memory(), torch.cuda.Event()))
+                hp, hf, ev = self._stage[-1]
+            else:
+                hp, hf, ev = self._stage[self._stage_i % 4]
+                ev.synchronize()                  # the copy that last used this slot has executed
+            self._stage_i += 1
+        alive = []
+        for i, c in enumerate(compute):
+            g = c.grad
+            if g is None:
+                raise RuntimeError(f"tensor {self.table.names[i]} received no gradient")
+            if g.stride() != c.stride() or g.dtype not in (torch.float32, torch.bfloat16):
+                g = torch.empty_like(c, dtype=g.dtype if g.dtype in (torch.float32, torch.bfloat16)
+                                     else torch.float32).copy_(g)
+            hp[i] = g.data_ptr()
+            hf[i] = 1 if g.dtype == torch.bfloat16 else 0
+            alive.append(g)
+        self.d_gptr.copy_(hp, non_blocking=True)
+        self.d_gbf16.copy_(hf, non_blocking=True)
+        if ev is not None:
+            ev.record()
+        self._grads_alive = alive                 # keep them until the next table replaces them
+        return hp, hf, alive
 
     # ------------------------------------------------------------------ step
     graph_safe = True      # launch() only enqueues kernels whose per-step state lives on the device
@@ -337,6 +386,8 @@ class P2PBackend(CommBackend):
             self.C.allreduce(self.ap_avg, self.grid, self._stream())
         if not self.cfg.final_divide_all and self.ring.rank != 0:
             self.arena.theta.mul_(float(self.ring.world))     # reference quirk Q5: only rank 0 divides
+        if self.table_mode and getattr(self.arena, "shadow", None) is not None:
+            self._init_norms(run_fsm=False)                   # refresh the bf16 shadow of the averaged model
 
     def final_average(self) -> None:
         self.final_average_nocheck()
