@@ -21,6 +21,17 @@
 
 namespace egb {
 
+// Per-CTA tile metadata, resolved ONCE at kernel start (thread j resolves iteration j, so the
+// dependent table look-ups tile->tensor->{fire, grad pointer, numel} run in parallel instead of
+// sitting on every iteration's critical path in front of the streaming loads).
+struct TileInfo {
+  const void* gptr;   // table mode: address of this tile's first gradient element (null: flat arena)
+  int tensor;
+  int valid;          // elements of the tensor left from this tile's start (>= EG_TILE: full tile)
+  int flags;          // bit0 fire, bit1 gradient is bf16
+};
+#define EG_TI_CACHE 64
+
 // -------------------------------------------------------------------------------------------
 // Trigger FSM update of ONE tensor for step `next_step` (scalar code, one lane).
 // Also accounts the messages of the step that just ran (fire[i] still holds that decision).
@@ -100,8 +111,8 @@ __device__ __forceinline__ double reduce_partials(const float* part, int n4, int
 // completes a tensor reduces that tensor's per-warp partials in fixed order (one warp per tensor)
 // and runs the trigger FSM for it.  Tiles of a CTA ascend, so equal tensors are consecutive.
 #define EG_MAX_OWN 1024   // >= number of parameter tensors (asserted host-side)
-__device__ __forceinline__ void cta_finish_tensors(const GossipParams& p, int next_step, bool count,
-                                                   bool recv_ok) {
+__device__ __forceinline__ void cta_finish_tensors(const GossipParams& p, const TileInfo* s_ti, int next_step,
+                                                   bool count, bool recv_ok) {
   __shared__ int s_own[EG_MAX_OWN];
   __shared__ int s_nown;
   const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -109,8 +120,9 @@ __device__ __forceinline__ void cta_finish_tensors(const GossipParams& p, int ne
   if (tid == 0) {
     __threadfence();
     int nown = 0, cur = -1, cnt = 0;
-    for (int t = b; ; t += G) {
-      const int i = (t < p.tab.n_tiles) ? p.tab.tile_tensor[t] : -2;
+    int j = 0;
+    for (int t = b; ; t += G, ++j) {
+      const int i = (t < p.tab.n_tiles) ? ((s_ti != nullptr && j < EG_TI_CACHE) ? s_ti[j].tensor : p.tab.tile_tensor[t]) : -2;
       if (i != cur) {
         if (cur >= 0) {
           const unsigned prev = atomicAdd(p.tensor_done + cur, (unsigned)cnt);
@@ -157,18 +169,44 @@ __device__ __forceinline__ void push_tile(const GossipParams& p, size_t base, co
   }
 }
 
-// Gradient of this thread's 8 elements.  Flat mode: the fp32 grad arena.  Table mode: autograd's
-// own gradient tensors are read in place through a per-tensor pointer table (bf16 or fp32, exactly
-// numel elements each) -- no AccumulateGrad kernels, no grad arena traffic, no zeroing.
-__device__ __forceinline__ F8 load_grad(const GossipParams& p, int t, size_t base, int tid) {
-  if (p.t_grad_ptr == nullptr) return ld_f8(p.grad + base);
+__device__ __forceinline__ TileInfo resolve_tile(const GossipParams& p, int t) {
+  TileInfo ti;
   const int i = p.tab.tile_tensor[t];
-  const int off = (t - p.tab.t_tile_start[i]) * EG_TILE + tid * EG_VEC;
-  const int numel = p.tab.t_numel[i];
+  const int first = (t - p.tab.t_tile_start[i]) * EG_TILE;
+  ti.tensor = i;
+  ti.valid = p.tab.t_numel[i] - first;
+  ti.flags = p.fsm.fire[i] ? 1 : 0;
+  ti.gptr = nullptr;
+  if (p.t_grad_ptr != nullptr) {
+    const bool bf = p.t_grad_bf16[i] != 0;
+    ti.flags |= bf ? 2 : 0;
+    ti.gptr = reinterpret_cast<const char*>(p.t_grad_ptr[i]) + (size_t)first * (bf ? 2 : 4);
+  }
+  return ti;
+}
+
+__device__ __forceinline__ void fill_tile_cache(const GossipParams& p, TileInfo* s_ti) {
+  const int j = threadIdx.x;
+  if (j < EG_TI_CACHE) {
+    const int t = blockIdx.x + j * gridDim.x;
+    if (t < p.tab.n_tiles) s_ti[j] = resolve_tile(p, t);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ TileInfo tile_info(const GossipParams& p, const TileInfo* s_ti, int j, int t) {
+  return (j < EG_TI_CACHE) ? s_ti[j] : resolve_tile(p, t);
+}
+
+// Gradient of this thread's 8 elements.  Flat mode: the fp32 grad arena.  Table mode: autograd's
+// own gradient tensors are read in place (bf16 or fp32, exactly numel elements each) -- no
+// AccumulateGrad kernels, no grad arena traffic, no zeroing.
+__device__ __forceinline__ F8 load_grad(const GossipParams& p, const TileInfo& ti, size_t base, int tid) {
+  if (ti.gptr == nullptr) return ld_f8(p.grad + base);
+  const int off = tid * EG_VEC;
   F8 g;
-  if (p.t_grad_bf16[i]) {
-    const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.t_grad_ptr[i]);
-    if (off + EG_VEC <= numel) {
+  if (ti.flags & 2) {
+    const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(ti.gptr);
+    if (off + EG_VEC <= ti.valid) {
       const uint4 u = *reinterpret_cast<const uint4*>(gp + off);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -179,17 +217,17 @@ __device__ __forceinline__ F8 load_grad(const GossipParams& p, int t, size_t bas
       }
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) g.v[e] = (off + e < numel) ? __bfloat162float(gp[off + e]) : 0.f;
+      for (int e = 0; e < 8; ++e) g.v[e] = (off + e < ti.valid) ? __bfloat162float(gp[off + e]) : 0.f;
     }
   } else {
-    const float* gp = reinterpret_cast<const float*>(p.t_grad_ptr[i]);
-    if (off + EG_VEC <= numel) {
+    const float* gp = reinterpret_cast<const float*>(ti.gptr);
+    if (off + EG_VEC <= ti.valid) {
       const float4 a = *reinterpret_cast<const float4*>(gp + off), b = *reinterpret_cast<const float4*>(gp + off + 4);
       g.v[0] = a.x; g.v[1] = a.y; g.v[2] = a.z; g.v[3] = a.w;
       g.v[4] = b.x; g.v[5] = b.y; g.v[6] = b.z; g.v[7] = b.w;
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) g.v[e] = (off + e < numel) ? gp[off + e] : 0.f;
+      for (int e = 0; e < 8; ++e) g.v[e] = (off + e < ti.valid) ? gp[off + e] : 0.f;
     }
   }
   return g;
@@ -197,8 +235,8 @@ __device__ __forceinline__ F8 load_grad(const GossipParams& p, int t, size_t bas
 
 // mix + SGD + norm-on-write for one tile. `th` already holds theta_k for this thread's 8 floats.
 template <bool kMom>
-__device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t base, F8 th, int lane,
-                                         int warp, int step) {
+__device__ __forceinline__ void mix_tile(const GossipParams& p, int t, const TileInfo& ti, size_t base, F8 th,
+                                         int lane, int warp, int step) {
   const bool logrecv = (p.tile_ss_l != nullptr);
   float ssl = 0.f, ssr = 0.f;
   // issue every load of the tile before the first dependent FP op (5 x 32 B in flight per lane)
@@ -207,7 +245,7 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
     L = ld_f8_cg(p.inbox_l + base);
     R = ld_f8_cg(p.inbox_r + base);
   }
-  const F8 g = load_grad(p, t, base, threadIdx.x);
+  const F8 g = load_grad(p, ti, base, threadIdx.x);
   if (kMom) m = ld_f8(p.mom + base);
   if (p.do_mix) {
 #pragma unroll
@@ -237,7 +275,7 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, size_t ba
   }
   st_f8(p.theta + base, th);
   if (p.shadow != nullptr) st_bf16x8(p.shadow + base, th);
-  if (p.zero_grad && p.t_grad_ptr == nullptr) {
+  if (p.zero_grad && ti.gptr == nullptr) {
     F8 z;
 #pragma unroll
     for (int e = 0; e < 8; ++e) z.v[e] = 0.f;
@@ -296,8 +334,11 @@ __device__ __forceinline__ void push_phase(const GossipParams& p, int step) {
     }
     __syncthreads();
   }
-  for (int t = b; t < p.tab.n_tiles; t += G) {
-    if (!p.fsm.fire[p.tab.tile_tensor[t]]) continue;
+  __shared__ TileInfo s_ti[EG_TI_CACHE];
+  fill_tile_cache(p, s_ti);
+  int j = 0;
+  for (int t = b; t < p.tab.n_tiles; t += G, ++j) {
+    if (!(tile_info(p, s_ti, j, t).flags & 1)) continue;
     const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
     push_tile(p, base, ld_f8(p.theta + base));
   }
@@ -328,6 +369,8 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
     push_phase(p, step);
     return;
   }
+  __shared__ TileInfo s_ti[EG_TI_CACHE];
+  fill_tile_cache(p, s_ti);
   if (p.phase == 2 && p.sync && p.do_push) {
     // split step, second half: the neighbours' pushes of this step were issued during my backward
     if (tid == 0) {
@@ -339,11 +382,13 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
 
   if (!(p.sync && push)) {
     // ---------------- async / split / no exchange: single pass, theta read once ---------------
-    for (int t = b; t < n_tiles; t += G) {
+    int j = 0;
+    for (int t = b; t < n_tiles; t += G, ++j) {
       const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+      const TileInfo ti = tile_info(p, s_ti, j, t);
       const F8 th = ld_f8(p.theta + base);
-      if (push && p.fsm.fire[p.tab.tile_tensor[t]]) push_tile(p, base, th);
-      mix_tile<kMom>(p, t, base, th, lane, warp, step);
+      if (push && (ti.flags & 1)) push_tile(p, base, th);
+      mix_tile<kMom>(p, t, ti, base, th, lane, warp, step);
     }
   } else {
     // ---------------- iter-sync: per-WARP software pipeline, no block barriers ------------------
@@ -365,7 +410,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
     for (int j = 0; j < iters + D; ++j) {
       const int t = b + j * G;
       if (j < iters && t < n_tiles) {
-        const bool fired = p.fsm.fire[p.tab.tile_tensor[t]] != 0;
+        const bool fired = (tile_info(p, s_ti, j, t).flags & 1) != 0;
         if (fired) {
           const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
           push_tile(p, base, ld_f8(p.theta + base));
@@ -385,11 +430,11 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
         }
         __syncwarp();
         const size_t base = (size_t)t2 * EG_TILE + (size_t)tid * EG_VEC;
-        mix_tile<kMom>(p, t2, base, ld_f8(p.theta + base), lane, warp, step);
+        mix_tile<kMom>(p, t2, tile_info(p, s_ti, j - D, t2), base, ld_f8(p.theta + base), lane, warp, step);
       }
     }
   }
-  if (p.need_norm) cta_finish_tensors(p, step + 1, p.do_mix != 0, true);
+  if (p.need_norm) cta_finish_tensors(p, s_ti, step + 1, p.do_mix != 0, true);
   grid_tail(p, step);
 }
 
@@ -416,7 +461,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_init_kernel(const Gossip
       }
     }
   }
-  if (run_fsm) cta_finish_tensors(p, next_step, false, /*recv_ok=*/false);
+  if (run_fsm) cta_finish_tensors(p, nullptr, next_step, false, /*recv_ok=*/false);
 }
 
 // Trigger FSM alone, norms supplied by the caller (unit test against parallel/trigger.py).

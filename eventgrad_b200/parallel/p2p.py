@@ -91,6 +91,9 @@ class P2PBackend(CommBackend):
         self.grid = min(t.n_tiles, symm["max_grid"])
         if grid_cap:
             self.grid = min(self.grid, grid_cap)
+        # balance: every CTA gets the same number of tiles (+-1 only on the last round)
+        rounds = -(-t.n_tiles // self.grid)
+        self.grid = -(-t.n_tiles // rounds)
         self.group_iters, self.timeout_ns, self.vec256_push = group_iters, timeout_ns, vec256_push
         self.sync = cfg.sync_mode == "iter"
         self.gossip = cfg.algo in ("decent", "event", "spevent")

@@ -25,7 +25,9 @@ def _run(world, *args, timeout=300):
 
 def _worlds():
     n = torch.cuda.device_count() if torch.cuda.is_available() else 0
-    return [w for w in (2, 4, 8) if w <= n]
+    want = os.environ.get("EGB_TEST_WORLDS")
+    cand = [int(x) for x in want.split(",")] if want else [2, 4, 8]
+    return [w for w in cand if w <= n]
 
 
 @pytest.mark.parametrize("algo", ["cent", "decent", "event", "spevent"])
