@@ -195,16 +195,20 @@ struct BnParams {
   long long* nbt;             // optional num_batches_tracked
   float* dgamma;              // backward outputs (fp32) -- also inputs of the dx kernel
   float* dbeta;
-  float* partial;             // workspace [bn_partial_rows][2*C]
-  unsigned int* ticket;
+  float* partial;             // workspace [bn_partial_rows][128]
+  unsigned int* ticket;       // [64]: per-slice tickets [0..31], global epoch ticket [63]
+  unsigned int* flag;         // [32] per-slice epoch flags (fused kernels)
+  unsigned int* epoch;        // [1]  launch epoch (device resident: graph-replay safe)
+  int* status;                // sticky error word (2 = fused-kernel wait timed out)
   long long M;
   int C;
   float eps;
   float momentum;
   int relu;
+  int fused_ok;               // allow the single-launch fused path when the grid is co-resident
 };
 int bn_partial_rows(int sm_count);
-// which: 0 fwd stats, 1 fwd apply, 2 bwd reduce, 3 bwd dx
+// which: 0 training forward, 1 apply only (eval), 2 backward
 cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------ IPC window runtime

@@ -87,6 +87,7 @@ static const std::unordered_map<std::string, Setter<BnParams>> kBn = {
     PTRF(BnParams, dres), PTRF(BnParams, gamma), PTRF(BnParams, beta), PTRF(BnParams, mean),
     PTRF(BnParams, invstd), PTRF(BnParams, run_mean), PTRF(BnParams, run_var), PTRF(BnParams, nbt),
     PTRF(BnParams, dgamma), PTRF(BnParams, dbeta), PTRF(BnParams, partial), PTRF(BnParams, ticket),
+    PTRF(BnParams, flag), PTRF(BnParams, epoch), PTRF(BnParams, status), NUMF(BnParams, fused_ok),
     NUMF(BnParams, M), NUMF(BnParams, C), NUMF(BnParams, eps), NUMF(BnParams, momentum), NUMF(BnParams, relu),
 };
 
@@ -159,10 +160,12 @@ PYBIND11_MODULE(_C, m) {
     check(launch_bn(p, which, sm_count, S(s)), "bn_launch");
   });
   // positional fast path (avoids the dict round trip on the per-layer hot path)
+  // positional fast paths (no dict round trip on the per-layer hot path).  ws = {partial, ticket, flag,
+  // epoch, status} device addresses of the shared workspace; `dir` 0 forward / 1 backward halves.
   m.def("bn_forward", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t gamma, uintptr_t beta, uintptr_t mean,
                          uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt, uintptr_t partial,
-                         uintptr_t ticket, long long M, int C, float eps, float momentum, int relu, int training,
-                         int sm_count, uintptr_t s) {
+                         uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
+                         float eps, float momentum, int relu, int training, int fused_ok, int sm_count, uintptr_t s) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
     p.x = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -177,13 +180,16 @@ PYBIND11_MODULE(_C, m) {
     p.nbt = reinterpret_cast<long long*>(nbt);
     p.partial = reinterpret_cast<float*>(partial);
     p.ticket = reinterpret_cast<unsigned int*>(ticket);
-    p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu;
-    if (training) check(launch_bn(p, 0, sm_count, S(s)), "bn_fwd_stats");
-    check(launch_bn(p, 1, sm_count, S(s)), "bn_fwd_apply");
+    p.flag = reinterpret_cast<unsigned int*>(flag);
+    p.epoch = reinterpret_cast<unsigned int*>(epoch);
+    p.status = reinterpret_cast<int*>(status);
+    p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu; p.fused_ok = fused_ok;
+    check(launch_bn(p, training ? 0 : 1, sm_count, S(s)), "bn_forward");
   });
   m.def("bn_backward", [](uintptr_t x, uintptr_t y, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
                           uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
-                          uintptr_t ticket, long long M, int C, int relu, int sm_count, uintptr_t s) {
+                          uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
+                          int relu, int fused_ok, int sm_count, uintptr_t s) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
     p.x = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -198,9 +204,11 @@ PYBIND11_MODULE(_C, m) {
     p.dbeta = reinterpret_cast<float*>(dbeta);
     p.partial = reinterpret_cast<float*>(partial);
     p.ticket = reinterpret_cast<unsigned int*>(ticket);
-    p.M = M; p.C = C; p.relu = relu;
-    check(launch_bn(p, 2, sm_count, S(s)), "bn_bwd_reduce");
-    check(launch_bn(p, 3, sm_count, S(s)), "bn_bwd_dx");
+    p.flag = reinterpret_cast<unsigned int*>(flag);
+    p.epoch = reinterpret_cast<unsigned int*>(epoch);
+    p.status = reinterpret_cast<int*>(status);
+    p.M = M; p.C = C; p.relu = relu; p.fused_ok = fused_ok;
+    check(launch_bn(p, 2, sm_count, S(s)), "bn_backward");
   });
   m.def("decode_augment",
         [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,

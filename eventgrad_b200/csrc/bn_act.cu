@@ -1,34 +1,38 @@
 // eventgrad_b200 -- fused BatchNorm2d (+ residual add) (+ ReLU), training forward + backward,
 // channels-last bf16 activations, fp32 statistics/parameters.  sm_100a.
 //
-// Why: a launch-level profile of the flagship step (CIFAR ResNet, batch 256, bf16 autocast,
-// profiles/launches_bench1_*.md) shows ATen's batch-norm + elementwise kernels taking ~2/3 of the
-// GPU time while the tcgen05 convolutions take under 1/3.  The block pattern of the reference's
-// ResNet (/root/reference/dcifar10/common/resnet.hpp:39-52: bn -> relu, bn -> += residual -> relu)
-// is memory-bound glue; here it is 2 streaming kernels forward and 2 backward:
+// Why: a launch-level profile of the flagship step (CIFAR ResNet, bf16 autocast, see profiles/)
+// shows ATen's batch-norm + elementwise kernels taking ~2/3 of the GPU time while the tcgen05
+// convolutions take under 1/3.  The block pattern of the reference's ResNet
+// (/root/reference/dcifar10/common/resnet.hpp:39-52: bn -> relu, bn -> += residual -> relu) is
+// memory-bound glue.
 //
-//   fwd  stats : per-channel sum / sum-of-squares partials over row slabs; the last CTA combines
-//                them in fixed order (double), writes mean / invstd, updates running stats
-//        apply : y = relu?( (x-mean)*invstd*gamma + beta (+ residual) )            -> bf16
-//   bwd  reduce: dz = relu? dy*(y>0) : dy ;  sum dz, sum dz*xhat  -> dbeta, dgamma
-//        dx    : dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) ; dres = dz -> bf16
+// Geometry.  NHWC == row-major [M = N*H*W, C].  The tensor is cut into C/64 channel SLICES; a CTA
+// works on one slice (blockIdx.y) and one row split (blockIdx.x): 8 threads x 8 channels (one
+// 128-byte line) per row, 32 rows per pass.  Per-slice partial sums are combined in fixed order by
+// the last CTA *of that slice*, so the combine work is spread over C/64 CTAs and is tiny.
 //
-// Layout: NHWC == row-major [M = N*H*W, C].  A thread owns 8 consecutive channels (one 16-byte
-// vector per row); TPR = C/8 threads span a row and 256/TPR rows are processed per CTA pass.
+// Two code paths, chosen per call by the tensor size:
+//   * FUSED (small/medium tensors -- the per-GPU tensors of the 8-GPU configuration): ONE kernel.
+//     Each CTA keeps its slab in registers, publishes its partials, waits on a per-slice epoch flag
+//     written by the slice's last CTA (all CTAs co-resident: grid <= 2 x SMs), then normalises the
+//     registers and stores.  x is read exactly once; forward = 1 launch, backward = 1 launch.
+//   * SPLIT (large tensors): stats kernel -> apply kernel; reduce kernel -> dx kernel.
 #include "api.h"
 #include "common.cuh"
 
 namespace egb {
 
 #define BN_THREADS 256
-#define BN_UNROLL 8
+#define BN_RPP 32            // rows per pass (256 threads / 8 threads per row)
+#define BN_SLICE 64          // channels per slice
+#define BN_FWD_PASSES 8      // slab depth held in registers by the fused forward
+#define BN_BWD_PASSES 4      // ... by the fused backward (3 tensors)
 
 struct V8 {
   float v[8];
 };
-
-__device__ __forceinline__ V8 load_bf16x8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ V8 unpack_bf16x8(const uint4& u) {
   V8 r;
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -39,83 +43,77 @@ __device__ __forceinline__ V8 load_bf16x8(const __nv_bfloat16* p) {
   }
   return r;
 }
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const V8& r) {
+__device__ __forceinline__ uint4 pack_bf16x8(const V8& r) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
+  return u;
 }
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& u) { *reinterpret_cast<uint4*>(p) = u; }
 
-// ---------------------------------------------------------------------------------------------
-// Block-level: reduce per-thread 2x8 accumulators over the row lanes (ty) and write this CTA's
-// partial [2][C] row; then the last CTA combines all partial rows in fixed order.
-// smem: [rows_per_pass][2*C] floats = 256/TPR * 16*TPR * 4 B = 16 KB for every C.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_partials(const float (&a)[8], const float (&b)[8], float* smem, int C,
-                                               int tx, int ty, int rpp, float* partial_row) {
-  float* row = smem + (size_t)ty * 2 * C;
+// -------------------------------------------------------------------------------------------
+// Reduce the per-thread 2x8 accumulators over the 32 row lanes, write this CTA's partial row
+// [128] = {sum a[64] | sum b[64]} for its slice.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_partials(const float (&a)[8], const float (&b)[8], float* smem /*[32][128]*/,
+                                               int tx, int ty, float* partial_row) {
+  float* row = smem + ty * 128;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     row[tx * 8 + e] = a[e];
-    row[C + tx * 8 + e] = b[e];
+    row[64 + tx * 8 + e] = b[e];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+  if (threadIdx.x < 128) {
     float s = 0.f;
-    for (int r = 0; r < rpp; ++r) s += smem[(size_t)r * 2 * C + c];
-    partial_row[c] = s;
+#pragma unroll 8
+    for (int r = 0; r < BN_RPP; ++r) s += smem[r * 128 + threadIdx.x];
+    partial_row[threadIdx.x] = s;
   }
 }
 
-// Last CTA: out[c] = sum_b partial[b][c] in double, fixed order.  All 256 threads take part:
-// thread = (float4 column, row lane); each walks its rows with 4 loads in flight, then the row
-// lanes are folded through shared memory in lane order.  smem needs lanes*W doubles.
-__device__ __forceinline__ void final_combine(const float* partial, int nb, int W, double* sm) {
-  const int W4 = W / 4;                                   // W = 2C is a multiple of 16
-  const int lanes = (BN_THREADS >= W4) ? BN_THREADS / W4 : 1;
-  for (int col0 = 0; col0 < W4; col0 += BN_THREADS) {     // only loops when W4 > 256 (C > 512)
-    const int col = col0 + (int)(threadIdx.x % (lanes > 1 ? W4 : BN_THREADS));
-    const int bl = (lanes > 1) ? (int)(threadIdx.x / W4) : 0;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    if (col < W4) {
-      const float4* p4 = reinterpret_cast<const float4*>(partial) + col;
-      int b = bl;
-      for (; b + 7 * lanes < nb; b += 8 * lanes) {
-        float4 x[8];
+// Last CTA of a slice: tot[c] = sum_r partial[r][c], fixed order, double.  256 threads = 32 float4
+// columns x 8 row lanes, 8 loads in flight each; lanes folded through smem (8 x 128 doubles).
+__device__ __forceinline__ void slice_combine(const float* partial, int nrows, double* sm /*[8][128]*/) {
+  const int col = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const float4* p4 = reinterpret_cast<const float4*>(partial) + col;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int r = bl;
+  for (; r + 56 < nrows; r += 64) {
+    float4 x[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = __ldcg(p4 + (size_t)(b + u * lanes) * W4);
+    for (int u = 0; u < 8; ++u) x[u] = __ldcg(p4 + (size_t)(r + 8 * u) * 32);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          a0 += (double)x[u].x; a1 += (double)x[u].y; a2 += (double)x[u].z; a3 += (double)x[u].w;
-        }
-      }
-      for (; b < nb; b += lanes) {
-        const float4 x0 = __ldcg(p4 + (size_t)b * W4);
-        a0 += (double)x0.x; a1 += (double)x0.y; a2 += (double)x0.z; a3 += (double)x0.w;
-      }
-      double* dst = sm + (size_t)bl * W + (size_t)col * 4;
-      dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+    for (int u = 0; u < 8; ++u) {
+      a0 += (double)x[u].x; a1 += (double)x[u].y; a2 += (double)x[u].z; a3 += (double)x[u].w;
     }
+  }
+  for (; r < nrows; r += 8) {
+    const float4 x0 = __ldcg(p4 + (size_t)r * 32);
+    a0 += (double)x0.x; a1 += (double)x0.y; a2 += (double)x0.z; a3 += (double)x0.w;
+  }
+  __syncthreads();                                        // smem is being re-purposed
+  double* dst = sm + bl * 128 + col * 4;
+  dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double t = sm[threadIdx.x];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) t += sm[l * 128 + threadIdx.x];
+    sm[threadIdx.x] = t;                                  // row 0 = totals
   }
   __syncthreads();
-  if (lanes > 1) {
-    for (int c = threadIdx.x; c < W; c += BN_THREADS) {
-      double t = sm[c];
-      for (int l = 1; l < lanes; ++l) t += sm[(size_t)l * W + c];
-      sm[c] = t;                                           // row 0 holds the totals
-    }
-    __syncthreads();
-  }
 }
 
-__device__ __forceinline__ bool elect_last_block(unsigned int* ticket) {
+__device__ __forceinline__ bool elect_last_of_slice(unsigned int* ticket, unsigned int n) {
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned prev = atomicAdd(ticket, 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    s_last = (prev == n - 1) ? 1 : 0;
     if (s_last) *ticket = 0u;
   }
   __syncthreads();
@@ -123,239 +121,428 @@ __device__ __forceinline__ bool elect_last_block(unsigned int* ticket) {
   return s_last != 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// forward statistics
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const BnParams p) {
-  extern __shared__ float smem[];
-  const int C = p.C, TPR = C / 8, rpp = BN_THREADS / TPR;
-  const int tx = threadIdx.x % TPR, ty = threadIdx.x / TPR;
+// mean / invstd / running stats for one slice from its totals (tot[0..63] = sum x, [64..127] = sum x^2)
+__device__ __forceinline__ void finalize_stats(const BnParams& p, int slice, const double* tot) {
+  if (threadIdx.x < BN_SLICE) {
+    const int c = slice * BN_SLICE + threadIdx.x;
+    const double invM = 1.0 / (double)p.M;
+    const double mean = tot[threadIdx.x] * invM;
+    double var = tot[64 + threadIdx.x] * invM - mean * mean;   // biased
+    if (var < 0.0) var = 0.0;
+    p.mean[c] = (float)mean;
+    p.invstd[c] = rsqrtf((float)var + p.eps);
+    if (p.run_mean != nullptr) {
+      const double unb = p.M > 1 ? var * (double)p.M / (double)(p.M - 1) : var;
+      p.run_mean[c] = (float)((1.0 - p.momentum) * (double)p.run_mean[c] + p.momentum * mean);
+      p.run_var[c] = (float)((1.0 - p.momentum) * (double)p.run_var[c] + p.momentum * unb);
+    }
+  }
+  if (threadIdx.x == 0 && slice == 0 && p.nbt != nullptr) *p.nbt += 1;
+}
+
+// epoch flag: slice-last CTA publishes, everyone else of the slice spins (bounded)
+__device__ __forceinline__ void publish_flag(unsigned int* flag, unsigned int value) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+  }
+}
+__device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int value, int* status) {
+  if (threadIdx.x == 0) {
+    const uint64_t t0 = globaltimer_ns();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if ((int)(v - value) >= 0) break;
+      if (globaltimer_ns() - t0 > 2000000000ull) {       // 2 s: co-residency assumption violated
+        if (status != nullptr) atomicExch(status, 2);
+        break;
+      }
+    } while (true);
+  }
+  __syncthreads();
+}
+
+// ===========================================================================================
+// FUSED forward: stats + normalise (+res)(+relu) in one launch, x read once
+// ===========================================================================================
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnParams p) {
+  __shared__ __align__(16) float smem[BN_RPP * 128];
+  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(p.epoch);
+  const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
+  uint4 xr[BN_FWD_PASSES];
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-  const long long stride = (long long)gridDim.x * rpp;
-  long long row = (long long)blockIdx.x * rpp + ty;
-  for (; row + (BN_UNROLL - 1) * stride < p.M; row += BN_UNROLL * stride) {
-    V8 x[BN_UNROLL];
+  const long long row0 = (long long)rs * (BN_FWD_PASSES * BN_RPP) + ty;
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) x[u] = load_bf16x8(p.x + (row + u * stride) * C + tx * 8);
-#pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s[e] += x[u].v[e];
-        q[e] = fmaf(x[u].v[e], x[u].v[e], q[e]);
-      }
+  for (int u = 0; u < BN_FWD_PASSES; ++u) {
+    const long long row = row0 + u * BN_RPP;
+    xr[u] = (row < p.M) ? ldg16(p.x + row * p.C + coff) : make_uint4(0, 0, 0, 0);
   }
-  for (; row < p.M; row += stride) {
-    const V8 x = load_bf16x8(p.x + row * C + tx * 8);
+#pragma unroll
+  for (int u = 0; u < BN_FWD_PASSES; ++u) {
+    const V8 x = unpack_bf16x8(xr[u]);                     // rows beyond M contribute exact zeros
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       s[e] += x.v[e];
       q[e] = fmaf(x.v[e], x.v[e], q[e]);
     }
   }
-  block_partials(s, q, smem, C, tx, ty, rpp, p.partial + (size_t)blockIdx.x * 2 * C);
-  if (!elect_last_block(p.ticket)) return;
-  double* tot = reinterpret_cast<double*>(smem);          // 2C doubles (launch_bn sizes smem for it)
-  final_combine(p.partial, gridDim.x, 2 * C, tot);
-  const double invM = 1.0 / (double)p.M;
-  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-    const double mean = tot[c] * invM;
-    double var = tot[C + c] * invM - mean * mean;            // biased variance
-    if (var < 0.0) var = 0.0;
-    p.mean[c] = (float)mean;
-    p.invstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
-    if (p.run_mean != nullptr) {                             // running stats (momentum, unbiased var)
-      const double unb = p.M > 1 ? var * (double)p.M / (double)(p.M - 1) : var;
-      p.run_mean[c] = (float)((1.0 - p.momentum) * (double)p.run_mean[c] + p.momentum * mean);
-      p.run_var[c] = (float)((1.0 - p.momentum) * (double)p.run_var[c] + p.momentum * unb);
+  float* prow = p.partial + ((size_t)slice * RS + rs) * 128;
+  block_partials(s, q, smem, tx, ty, prow);
+  if (elect_last_of_slice(p.ticket + slice, RS)) {
+    double* tot = reinterpret_cast<double*>(smem);          // 8*128 doubles = 8 KB <= 16 KB
+    slice_combine(p.partial + (size_t)slice * RS * 128, RS, tot);
+    finalize_stats(p, slice, tot);
+    publish_flag(p.flag + slice, epoch + 1u);
+    if (threadIdx.x == 0) {                                 // global epoch bump by the last slice to finish
+      const unsigned prev = atomicAdd(p.ticket + 63, 1u);
+      if (prev == gridDim.y - 1) {
+        p.ticket[63] = 0u;
+        *p.epoch = epoch + 1u;
+      }
     }
   }
-  if (threadIdx.x == 0 && p.nbt != nullptr) *p.nbt += 1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward apply: y = act(x*scale + shift (+res))
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BN_THREADS) bn_fwd_apply_kernel(const BnParams p) {
-  const int C = p.C, TPR = C / 8, rpp = BN_THREADS / TPR;
-  const int tx = threadIdx.x % TPR, ty = threadIdx.x / TPR;
+  wait_flag(p.flag + slice, epoch + 1u, p.status);
   float sc[8], sh[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = tx * 8 + e;
-    sc[e] = p.gamma[c] * p.invstd[c];
-    sh[e] = p.beta[c] - p.mean[c] * sc[e];
+    const int c = slice * BN_SLICE + tx * 8 + e;
+    const float mean = __ldcg(p.mean + c), is = __ldcg(p.invstd + c);
+    sc[e] = p.gamma[c] * is;
+    sh[e] = p.beta[c] - mean * sc[e];
   }
-  const long long stride = (long long)gridDim.x * rpp;
   const bool has_res = p.res != nullptr;
-  for (long long row = (long long)blockIdx.x * rpp + ty; row < p.M; row += 2 * stride) {
-    const long long row2 = row + stride;
-    const bool two = row2 < p.M;
-    const size_t o1 = (size_t)row * C + tx * 8, o2 = (size_t)row2 * C + tx * 8;
-    V8 x1 = load_bf16x8(p.x + o1), x2, r1, r2;
-    if (two) x2 = load_bf16x8(p.x + o2);
-    if (has_res) {
-      r1 = load_bf16x8(p.res + o1);
-      if (two) r2 = load_bf16x8(p.res + o2);
-    }
+#pragma unroll
+  for (int u = 0; u < BN_FWD_PASSES; ++u) {
+    const long long row = row0 + u * BN_RPP;
+    if (row >= p.M) continue;
+    V8 x = unpack_bf16x8(xr[u]);
+    V8 r;
+    if (has_res) r = unpack_bf16x8(ldg16(p.res + row * p.C + coff));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float v = fmaf(x1.v[e], sc[e], sh[e]);
-      if (has_res) v += r1.v[e];
-      x1.v[e] = p.relu ? fmaxf(v, 0.f) : v;
+      float v = fmaf(x.v[e], sc[e], sh[e]);
+      if (has_res) v += r.v[e];
+      x.v[e] = p.relu ? fmaxf(v, 0.f) : v;
     }
-    store_bf16x8(p.y + o1, x1);
-    if (two) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float v = fmaf(x2.v[e], sc[e], sh[e]);
-        if (has_res) v += r2.v[e];
-        x2.v[e] = p.relu ? fmaxf(v, 0.f) : v;
-      }
-      store_bf16x8(p.y + o2, x2);
-    }
+    stg16(p.y + row * p.C + coff, pack_bf16x8(x));
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// backward reduce: sum dz, sum dz*xhat   (dz = relu-masked dy)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParams p) {
-  extern __shared__ float smem[];
-  const int C = p.C, TPR = C / 8, rpp = BN_THREADS / TPR;
-  const int tx = threadIdx.x % TPR, ty = threadIdx.x / TPR;
+// ===========================================================================================
+// FUSED backward: reduce + dx (+dres) in one launch
+// ===========================================================================================
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnParams p) {
+  __shared__ __align__(16) float smem[BN_RPP * 128];
+  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(p.epoch);
+  const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
   float mu[8], is[8], s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    mu[e] = p.mean[tx * 8 + e];
-    is[e] = p.invstd[tx * 8 + e];
+    mu[e] = p.mean[slice * BN_SLICE + tx * 8 + e];
+    is[e] = p.invstd[slice * BN_SLICE + tx * 8 + e];
     s1[e] = s2[e] = 0.f;
   }
-  const long long stride = (long long)gridDim.x * rpp;
-  for (long long row = (long long)blockIdx.x * rpp + ty; row < p.M; row += 2 * stride) {
-    const long long row2 = row + stride;
-    const bool two = row2 < p.M;
-    const size_t o1 = (size_t)row * C + tx * 8, o2 = (size_t)row2 * C + tx * 8;
-    V8 d1 = load_bf16x8(p.dy + o1), x1 = load_bf16x8(p.x + o1), y1, d2, x2, y2;
-    if (p.relu) y1 = load_bf16x8(p.y + o1);
-    if (two) {
-      d2 = load_bf16x8(p.dy + o2);
-      x2 = load_bf16x8(p.x + o2);
-      if (p.relu) y2 = load_bf16x8(p.y + o2);
+  uint4 dzr[BN_BWD_PASSES], xr[BN_BWD_PASSES];
+  const long long row0 = (long long)rs * (BN_BWD_PASSES * BN_RPP) + ty;
+#pragma unroll
+  for (int u = 0; u < BN_BWD_PASSES; ++u) {
+    const long long row = row0 + u * BN_RPP;
+    const bool ok = row < p.M;
+    uint4 d = ok ? ldg16(p.dy + row * p.C + coff) : make_uint4(0, 0, 0, 0);
+    xr[u] = ok ? ldg16(p.x + row * p.C + coff) : make_uint4(0, 0, 0, 0);
+    if (p.relu && ok) {                                     // dz = dy * (y > 0): fold the mask into dz now
+      const uint4 yy = ldg16(p.y + row * p.C + coff);
+      const unsigned short* ys = reinterpret_cast<const unsigned short*>(&yy);
+      unsigned short* ds = reinterpret_cast<unsigned short*>(&d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if ((ys[e] & 0x8000u) || (ys[e] & 0x7fffu) == 0u) ds[e] = 0;   // y <= 0 (bf16 sign / zero test)
     }
+    dzr[u] = d;
+  }
+#pragma unroll
+  for (int u = 0; u < BN_BWD_PASSES; ++u) {
+    const V8 dz = unpack_bf16x8(dzr[u]), x = unpack_bf16x8(xr[u]);
+    const bool ok = (row0 + u * BN_RPP) < p.M;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float dz = (p.relu && !(y1.v[e] > 0.f)) ? 0.f : d1.v[e];
-      s1[e] += dz;
-      s2[e] = fmaf(dz, (x1.v[e] - mu[e]) * is[e], s2[e]);
+      s1[e] += dz.v[e];
+      s2[e] = fmaf(dz.v[e], ok ? (x.v[e] - mu[e]) * is[e] : 0.f, s2[e]);
     }
-    if (two) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float dz = (p.relu && !(y2.v[e] > 0.f)) ? 0.f : d2.v[e];
-        s1[e] += dz;
-        s2[e] = fmaf(dz, (x2.v[e] - mu[e]) * is[e], s2[e]);
+  }
+  float* prow = p.partial + ((size_t)slice * RS + rs) * 128;
+  block_partials(s1, s2, smem, tx, ty, prow);
+  if (elect_last_of_slice(p.ticket + slice, RS)) {
+    double* tot = reinterpret_cast<double*>(smem);
+    slice_combine(p.partial + (size_t)slice * RS * 128, RS, tot);
+    if (threadIdx.x < BN_SLICE) {
+      p.dbeta[slice * BN_SLICE + threadIdx.x] = (float)tot[threadIdx.x];
+      p.dgamma[slice * BN_SLICE + threadIdx.x] = (float)tot[64 + threadIdx.x];
+    }
+    publish_flag(p.flag + slice, epoch + 1u);
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(p.ticket + 63, 1u);
+      if (prev == gridDim.y - 1) {
+        p.ticket[63] = 0u;
+        *p.epoch = epoch + 1u;
       }
     }
   }
-  block_partials(s1, s2, smem, C, tx, ty, rpp, p.partial + (size_t)blockIdx.x * 2 * C);
-  if (!elect_last_block(p.ticket)) return;
-  double* tot = reinterpret_cast<double*>(smem);
-  final_combine(p.partial, gridDim.x, 2 * C, tot);
-  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-    p.dbeta[c] = (float)tot[c];
-    p.dgamma[c] = (float)tot[C + c];
+  wait_flag(p.flag + slice, epoch + 1u, p.status);
+  float k0[8], k1[8], k2[8];
+  const float invM = 1.f / (float)p.M;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = slice * BN_SLICE + tx * 8 + e;
+    k0[e] = p.gamma[c] * is[e];
+    k1[e] = __ldcg(p.dbeta + c) * invM;
+    k2[e] = __ldcg(p.dgamma + c) * invM;
+  }
+  const bool want_dres = p.dres != nullptr;
+#pragma unroll
+  for (int u = 0; u < BN_BWD_PASSES; ++u) {
+    const long long row = row0 + u * BN_RPP;
+    if (row >= p.M) continue;
+    const V8 dz = unpack_bf16x8(dzr[u]);
+    V8 x = unpack_bf16x8(xr[u]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x.v[e] = k0[e] * (dz.v[e] - k1[e] - (x.v[e] - mu[e]) * is[e] * k2[e]);
+    stg16(p.dx + row * p.C + coff, pack_bf16x8(x));
+    if (want_dres) stg16(p.dres + row * p.C + coff, dzr[u]);
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// backward dx (+ dres)
-// ---------------------------------------------------------------------------------------------
+// ===========================================================================================
+// SPLIT path (large tensors)
+// ===========================================================================================
+__global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const BnParams p) {
+  __shared__ __align__(16) float smem[BN_RPP * 128];
+  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  const long long stride = (long long)RS * BN_RPP;
+  long long row = (long long)rs * BN_RPP + ty;
+  for (; row + 7 * stride < p.M; row += 8 * stride) {
+    uint4 xr[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xr[u] = ldg16(p.x + (row + u * stride) * p.C + coff);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const V8 x = unpack_bf16x8(xr[u]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += x.v[e];
+        q[e] = fmaf(x.v[e], x.v[e], q[e]);
+      }
+    }
+  }
+  for (; row < p.M; row += stride) {
+    const V8 x = unpack_bf16x8(ldg16(p.x + row * p.C + coff));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] += x.v[e];
+      q[e] = fmaf(x.v[e], x.v[e], q[e]);
+    }
+  }
+  block_partials(s, q, smem, tx, ty, p.partial + ((size_t)slice * RS + rs) * 128);
+  if (!elect_last_of_slice(p.ticket + slice, RS)) return;
+  double* tot = reinterpret_cast<double*>(smem);
+  slice_combine(p.partial + (size_t)slice * RS * 128, RS, tot);
+  finalize_stats(p, slice, tot);
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_fwd_apply_kernel(const BnParams p) {
+  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = slice * BN_SLICE + tx * 8 + e;
+    sc[e] = p.gamma[c] * p.invstd[c];
+    sh[e] = p.beta[c] - p.mean[c] * sc[e];
+  }
+  const long long stride = (long long)RS * BN_RPP;
+  const bool has_res = p.res != nullptr;
+  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += 4 * stride) {
+    uint4 xr[4], rr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r2 = row + u * stride;
+      if (r2 < p.M) {
+        xr[u] = ldg16(p.x + r2 * p.C + coff);
+        if (has_res) rr[u] = ldg16(p.res + r2 * p.C + coff);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r2 = row + u * stride;
+      if (r2 >= p.M) continue;
+      V8 x = unpack_bf16x8(xr[u]);
+      V8 r;
+      if (has_res) r = unpack_bf16x8(rr[u]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = fmaf(x.v[e], sc[e], sh[e]);
+        if (has_res) v += r.v[e];
+        x.v[e] = p.relu ? fmaxf(v, 0.f) : v;
+      }
+      stg16(p.y + r2 * p.C + coff, pack_bf16x8(x));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParams p) {
+  __shared__ __align__(16) float smem[BN_RPP * 128];
+  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
+  float mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mu[e] = p.mean[slice * BN_SLICE + tx * 8 + e];
+    is[e] = p.invstd[slice * BN_SLICE + tx * 8 + e];
+    s1[e] = s2[e] = 0.f;
+  }
+  const long long stride = (long long)RS * BN_RPP;
+  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += 3 * stride) {
+    uint4 dr[3], xr[3], yr[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const long long r2 = row + u * stride;
+      if (r2 < p.M) {
+        dr[u] = ldg16(p.dy + r2 * p.C + coff);
+        xr[u] = ldg16(p.x + r2 * p.C + coff);
+        if (p.relu) yr[u] = ldg16(p.y + r2 * p.C + coff);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (row + u * stride >= p.M) continue;
+      const V8 d = unpack_bf16x8(dr[u]), x = unpack_bf16x8(xr[u]);
+      V8 y;
+      if (p.relu) y = unpack_bf16x8(yr[u]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dz = (p.relu && !(y.v[e] > 0.f)) ? 0.f : d.v[e];
+        s1[e] += dz;
+        s2[e] = fmaf(dz, (x.v[e] - mu[e]) * is[e], s2[e]);
+      }
+    }
+  }
+  block_partials(s1, s2, smem, tx, ty, p.partial + ((size_t)slice * RS + rs) * 128);
+  if (!elect_last_of_slice(p.ticket + slice, RS)) return;
+  double* tot = reinterpret_cast<double*>(smem);
+  slice_combine(p.partial + (size_t)slice * RS * 128, RS, tot);
+  if (threadIdx.x < BN_SLICE) {
+    p.dbeta[slice * BN_SLICE + threadIdx.x] = (float)tot[threadIdx.x];
+    p.dgamma[slice * BN_SLICE + threadIdx.x] = (float)tot[64 + threadIdx.x];
+  }
+}
+
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_dx_kernel(const BnParams p) {
-  const int C = p.C, TPR = C / 8, rpp = BN_THREADS / TPR;
-  const int tx = threadIdx.x % TPR, ty = threadIdx.x / TPR;
+  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
   float mu[8], is[8], k0[8], k1[8], k2[8];
   const float invM = 1.f / (float)p.M;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = tx * 8 + e;
+    const int c = slice * BN_SLICE + tx * 8 + e;
     mu[e] = p.mean[c];
     is[e] = p.invstd[c];
     k0[e] = p.gamma[c] * is[e];              // dx = k0*(dz - k1 - xhat*k2)
     k1[e] = p.dbeta[c] * invM;
     k2[e] = p.dgamma[c] * invM;
   }
-  const long long stride = (long long)gridDim.x * rpp;
+  const long long stride = (long long)RS * BN_RPP;
   const bool want_dres = p.dres != nullptr;
-  for (long long row = (long long)blockIdx.x * rpp + ty; row < p.M; row += 2 * stride) {
-    const long long row2 = row + stride;
-    const bool two = row2 < p.M;
-    const size_t o1 = (size_t)row * C + tx * 8, o2 = (size_t)row2 * C + tx * 8;
-    V8 d1 = load_bf16x8(p.dy + o1), x1 = load_bf16x8(p.x + o1), y1, d2, x2, y2;
-    if (p.relu) y1 = load_bf16x8(p.y + o1);
-    if (two) {
-      d2 = load_bf16x8(p.dy + o2);
-      x2 = load_bf16x8(p.x + o2);
-      if (p.relu) y2 = load_bf16x8(p.y + o2);
+  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += 2 * stride) {
+    uint4 dr[2], xr[2], yr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long r2 = row + u * stride;
+      if (r2 < p.M) {
+        dr[u] = ldg16(p.dy + r2 * p.C + coff);
+        xr[u] = ldg16(p.x + r2 * p.C + coff);
+        if (p.relu) yr[u] = ldg16(p.y + r2 * p.C + coff);
+      }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float dz = (p.relu && !(y1.v[e] > 0.f)) ? 0.f : d1.v[e];
-      d1.v[e] = dz;
-      x1.v[e] = k0[e] * (dz - k1[e] - (x1.v[e] - mu[e]) * is[e] * k2[e]);
-    }
-    store_bf16x8(p.dx + o1, x1);
-    if (want_dres) store_bf16x8(p.dres + o1, d1);
-    if (two) {
+    for (int u = 0; u < 2; ++u) {
+      const long long r2 = row + u * stride;
+      if (r2 >= p.M) continue;
+      V8 d = unpack_bf16x8(dr[u]), x = unpack_bf16x8(xr[u]), y;
+      if (p.relu) y = unpack_bf16x8(yr[u]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float dz = (p.relu && !(y2.v[e] > 0.f)) ? 0.f : d2.v[e];
-        d2.v[e] = dz;
-        x2.v[e] = k0[e] * (dz - k1[e] - (x2.v[e] - mu[e]) * is[e] * k2[e]);
+        const float dz = (p.relu && !(y.v[e] > 0.f)) ? 0.f : d.v[e];
+        d.v[e] = dz;
+        x.v[e] = k0[e] * (dz - k1[e] - (x.v[e] - mu[e]) * is[e] * k2[e]);
       }
-      store_bf16x8(p.dx + o2, x2);
-      if (want_dres) store_bf16x8(p.dres + o2, d2);
+      stg16(p.dx + r2 * p.C + coff, pack_bf16x8(x));
+      if (want_dres) stg16(p.dres + r2 * p.C + coff, pack_bf16x8(d));
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-static int bn_grid(const BnParams& p, int max_ctas, int rows_per_cta_min) {
-  const int TPR = p.C / 8, rpp = BN_THREADS / TPR;
-  long long passes = (p.M + rpp - 1) / rpp;
-  long long g = (passes + rows_per_cta_min - 1) / rows_per_cta_min;
-  if (g < 1) g = 1;
-  if (g > max_ctas) g = max_ctas;
-  return (int)g;
-}
+// -------------------------------------------------------------------------------------------
+int bn_partial_rows(int sm_count) { return sm_count * 4 + 64; }   // max total CTAs of a reduction launch
 
-int bn_partial_rows(int sm_count) { return sm_count * 4; }
+static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
+// which: 0 training forward (stats [+ apply]), 1 apply only (eval), 2 backward
 cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s) {
-  const int TPR = p.C / 8;
-  if (p.C % 8 != 0 || TPR < 1 || TPR > BN_THREADS || (BN_THREADS % TPR) != 0) return cudaErrorInvalidValue;
-  size_t smem = (size_t)(BN_THREADS / TPR) * 2 * p.C * sizeof(float);   // 16 KB staging
-  {   // final combine: lanes * 2C doubles
-    const int W4 = 2 * p.C / 4;
-    const int lanes = (BN_THREADS >= W4) ? BN_THREADS / W4 : 1;
-    const size_t need = (size_t)lanes * 2 * p.C * sizeof(double);
-    if (smem < need) smem = need;
-  }
-  // reductions: few, fat CTAs (8 x 16 B loads in flight per thread) keep the fixed-order combine of
-  // the partial rows short: rows * 2C is bounded by ~32K floats
-  int red_cap = 32768 / (2 * p.C);
-  if (red_cap > bn_partial_rows(sm_count)) red_cap = bn_partial_rows(sm_count);
-  if (red_cap < 16) red_cap = 16;
-  const int red_grid = bn_grid(p, red_cap, 8);
-  const int map_grid = bn_grid(p, sm_count * 8, 4);
-  switch (which) {
-    case 0: bn_fwd_stats_kernel<<<red_grid, BN_THREADS, smem, s>>>(p); break;
-    case 1: bn_fwd_apply_kernel<<<map_grid, BN_THREADS, 0, s>>>(p); break;
-    case 2: bn_bwd_reduce_kernel<<<red_grid, BN_THREADS, smem, s>>>(p); break;
-    case 3: bn_bwd_dx_kernel<<<map_grid, BN_THREADS, 0, s>>>(p); break;
-    default: return cudaErrorInvalidValue;
+  if (p.C % BN_SLICE != 0 || p.C / BN_SLICE > 32 || p.M < 1) return cudaErrorInvalidValue;
+  const int slices = p.C / BN_SLICE;
+  const long long passes = ceil_div(p.M, BN_RPP);
+  const int max_ctas = 2 * sm_count;                       // co-residency bound of the fused kernels
+  const int split_cap = bn_partial_rows(sm_count) - 64;    // total CTAs of a split reduction
+  auto map_grid = [&](int rows_per_cta_passes) {
+    long long rsn = ceil_div(passes, rows_per_cta_passes);
+    const long long cap = (long long)(8 * sm_count) / slices;
+    if (rsn > cap) rsn = cap;
+    if (rsn < 1) rsn = 1;
+    return dim3((unsigned)rsn, (unsigned)slices);
+  };
+  auto red_grid = [&]() {
+    long long rsn = ceil_div(passes, 8);
+    const long long cap = (long long)split_cap / slices;
+    if (rsn > cap) rsn = cap;
+    if (rsn < 1) rsn = 1;
+    return dim3((unsigned)rsn, (unsigned)slices);
+  };
+  if (which == 0) {
+    const long long rs_f = ceil_div(passes, BN_FWD_PASSES);
+    if (p.fused_ok && rs_f * slices <= max_ctas) {
+      bn_fwd_fused_kernel<<<dim3((unsigned)rs_f, (unsigned)slices), BN_THREADS, 0, s>>>(p);
+    } else {
+      bn_fwd_stats_kernel<<<red_grid(), BN_THREADS, 0, s>>>(p);
+      bn_fwd_apply_kernel<<<map_grid(4), BN_THREADS, 0, s>>>(p);
+    }
+  } else if (which == 1) {
+    bn_fwd_apply_kernel<<<map_grid(4), BN_THREADS, 0, s>>>(p);
+  } else if (which == 2) {
+    const long long rs_b = ceil_div(passes, BN_BWD_PASSES);
+    if (p.fused_ok && rs_b * slices <= max_ctas) {
+      bn_bwd_fused_kernel<<<dim3((unsigned)rs_b, (unsigned)slices), BN_THREADS, 0, s>>>(p);
+    } else {
+      bn_bwd_reduce_kernel<<<red_grid(), BN_THREADS, 0, s>>>(p);
+      bn_bwd_dx_kernel<<<map_grid(2), BN_THREADS, 0, s>>>(p);
+    }
+  } else {
+    return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }

@@ -27,8 +27,15 @@ def _workspace(device):
         C = ext()
         sm = torch.cuda.get_device_properties(device).multi_processor_count
         rows = C.bn_partial_rows(sm)
-        ws = {"sm": sm, "partial": torch.empty(rows * 2 * 2048, dtype=torch.float32, device=device),
-              "ticket": torch.zeros(4, dtype=torch.int32, device=device), "C": C}
+        ctl = torch.zeros(512, dtype=torch.int32, device=device)   # tickets / flags / epochs / status
+        ws = {"sm": sm, "partial": torch.empty(rows * 128, dtype=torch.float32, device=device), "ctl": ctl,
+              # forward half | backward half: ticket[64], flag[32], epoch[1]
+              "f": (ctl[0:].data_ptr(), ctl[128:].data_ptr(), ctl[192:].data_ptr()),
+              "b": (ctl[64:].data_ptr(), ctl[160:].data_ptr(), ctl[200:].data_ptr()),
+              "status": ctl[256:].data_ptr(), "C": C,
+              # single-launch (spin-flag) variant for small tensors: measured SLOWER than the two-launch
+              # split path inside a CUDA graph (1.52 vs 1.42 ms/step at batch 32), so it is opt-in
+              "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0}
         _WS[device] = ws
     return ws
 
@@ -39,7 +46,7 @@ def _eligible(x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
     if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
         return False
     C = x.shape[1]
-    if C % 8 or C > 2048 or (256 % (C // 8)):
+    if C % 64 or C > 2048:
         return False
     if not x.is_contiguous(memory_format=torch.channels_last):
         return False
@@ -71,8 +78,9 @@ class _FusedBNActFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             C_ext.bn_forward(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
                              weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm, rv, nb,
-                             ws["partial"].data_ptr(), ws["ticket"].data_ptr(), M, C, float(eps),
-                             float(momentum), 1 if relu else 0, 1 if training else 0, ws["sm"], stream)
+                             ws["partial"].data_ptr(), ws["f"][0], ws["f"][1], ws["f"][2], ws["status"], M, C,
+                             float(eps), float(momentum), 1 if relu else 0, 1 if training else 0, ws["fused"],
+                             ws["sm"], stream)
         ctx.save_for_backward(x, y, weight, mean, invstd)
         ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
         return y
@@ -97,7 +105,8 @@ class _FusedBNActFn(torch.autograd.Function):
             C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                               dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
                               invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws["partial"].data_ptr(),
-                              ws["ticket"].data_ptr() + 4, M, C, 1 if ctx.relu else 0, ws["sm"], stream)
+                              ws["b"][0], ws["b"][1], ws["b"][2], ws["status"], M, C, 1 if ctx.relu else 0,
+                              ws["fused"], ws["sm"], stream)
         return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
 
 
@@ -120,3 +129,9 @@ class FusedBNAct(nn.BatchNorm2d):
             self.num_batches_tracked.add_(1)
         return bn_act_reference(x, self.weight, self.bias, self.running_mean, self.running_var, residual,
                                 training, self.momentum if self.momentum is not None else 0.0, self.eps, relu)
+
+
+def bn_status(device) -> int:
+    """Sticky status word of the fused BN kernels on `device` (0 ok, 2 = a flag wait timed out)."""
+    ws = _WS.get(torch.device(device))
+    return 0 if ws is None else int(ws["ctl"][256].item())
