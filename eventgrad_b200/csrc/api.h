@@ -211,6 +211,19 @@ int bn_partial_rows(int sm_count);
 // which: 0 training forward, 1 apply only (eval), 2 backward
 cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s);
 
+// ------------------------------------------------------------------ tcgen05 fused Linear(+bias)(+ReLU)
+// Y[M,N] = act(X[M,K] * W[N,K]^T + b): bf16 operands, fp32 accumulation in TMEM (csrc/linear_tc.cu).
+struct LinearParams {
+  const __nv_bfloat16* x;   // [M, K] row-major
+  const __nv_bfloat16* w;   // [N, K] row-major (nn.Linear weight layout)
+  const float* bias;        // [N] or null
+  void* y;                  // [M, N] bf16 or fp32
+  int M, N, K;              // N % 16 == 0, 16 <= N <= 256, K % 8 == 0
+  int relu;
+  int out_bf16;
+};
+cudaError_t launch_linear_tc(const LinearParams& p, cudaStream_t s);
+
 // ------------------------------------------------------------------ IPC window runtime
 // The RMA-window replacement (MPI_Alloc_mem + MPI_Win_create, event.cpp:138-147).
 struct IpcHandle {
