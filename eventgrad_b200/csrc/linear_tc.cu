@@ -10,6 +10,10 @@
 //   * operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout
 //     [K/8 chunk][row][8 elements]: a core matrix = 8 rows x 16 bytes, contiguous (128 B);
 //     SBO (next 8-row group) = 128 B, LBO (next 8-element K chunk) = rows*16 B;
+//   * warp-specialised: warps 1-3 are producers that keep a 3-stage cp.async (LDGSTS) ring full, each
+//     thread arriving on the stage's FULL mbarrier via cp.async.mbarrier.arrive; warp 0 / lane 0 is the
+//     MMA issuer and returns slots through EMPTY mbarriers with tcgen05.commit -- no __syncthreads in
+//     the main loop, MMAs issue back to back as stages fill;
 //   * one elected thread issues `tcgen05.mma.cta_group::1.kind::f16` (M=128, N<=256, K=16 per
 //     instruction) with 64-bit shared-memory descriptors and a 32-bit instruction descriptor;
 //     completion is tracked with `tcgen05.commit` -> mbarrier;
@@ -23,7 +27,8 @@
 namespace egb {
 
 #define LT_TM 128          // rows per CTA == UMMA M
-#define LT_BK 64           // K elements staged per round (4 UMMA k-steps of 16)
+#define LT_BK 32           // K elements per pipeline stage (2 UMMA k-steps of 16)
+#define LT_STAGES 3        // cp.async ring depth: 3 x 16 KB (N=128) = 48 KB -> 4 CTAs/SM, one wave for M=60000
 #define LT_THREADS 128
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,18 +68,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 
+// 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills (rows >= M, K tail)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 template <bool kOutBf16>
 __global__ void __launch_bounds__(LT_THREADS) linear_tc_kernel(const LinearParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K = p.K;
   const int row0 = blockIdx.x * LT_TM;
-  // smem carve-up: A tile [8 chunks][128 rows][16 B] = 16 KB | B tile [8][N][16 B] | mbarrier | tmem ptr
-  unsigned char* sA = smem_raw;
-  unsigned char* sB = smem_raw + (LT_BK / 8) * LT_TM * 16;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (LT_BK / 8) * N * 16);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  const uint32_t bar_a = smem_u32(bar);
+  // smem: LT_STAGES x { A tile [BK/8 chunks][128 rows][16 B] | B tile [BK/8][N][16 B] } | mbarriers | tmem ptr
+  constexpr int CH = LT_BK / 8;
+  constexpr int NPROD = LT_THREADS - 32;                       // warps 1..3 produce, warp 0 issues MMAs
+  const uint32_t a_bytes = CH * LT_TM * 16, b_bytes = (uint32_t)CH * N * 16;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + LT_STAGES * stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LT_STAGES + 1);
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * LT_STAGES, done_bar = empty0 + 8u * LT_STAGES;
   const uint32_t ncols = (N <= 32) ? 32u : (N <= 64) ? 64u : (N <= 128) ? 128u : 256u;
 
   if (warp == 0) {
@@ -83,44 +96,57 @@ __global__ void __launch_bounds__(LT_THREADS) linear_tc_kernel(const LinearParam
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) {
-    mbar_init(bar_a, 1);
+    for (int i = 0; i < LT_STAGES; ++i) {
+      mbar_init(full0 + 8u * i, NPROD);       // one cp.async-completion arrival per producer thread
+      mbar_init(empty0 + 8u * i, 1);          // one tcgen05.commit arrival
+    }
+    mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  const uint32_t idesc = make_instr_desc(N);
-
   const int num_kb = (K + LT_BK - 1) / LT_BK;
-  uint32_t parity = 0;
-  for (int kb = 0; kb < num_kb; ++kb) {
-    const int k0 = kb * LT_BK;
-    // ---- stage A (128 x 64) and B (N x 64): 8 consecutive threads fetch one 128-byte row segment ----
-    for (int idx = tid; idx < LT_TM * (LT_BK / 8); idx += LT_THREADS) {
-      const int r = idx >> 3, c = idx & 7;
-      const int gr = row0 + r, gk = k0 + c * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (gr < p.M && gk < K) v = *reinterpret_cast<const uint4*>(p.x + (size_t)gr * K + gk);
-      *reinterpret_cast<uint4*>(sA + ((size_t)c * LT_TM + r) * 16) = v;
+
+  if (warp >= 1) {
+    // ===== PRODUCERS: keep LT_STAGES k-blocks of LDGSTS copies in flight; never touch registers ====
+    const int ptid = tid - 32;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int st = kb % LT_STAGES;
+      if (kb >= LT_STAGES) mbar_wait(empty0 + 8u * st, (uint32_t)((kb / LT_STAGES - 1) & 1));   // MMAs freed the slot
+      const int k0 = kb * LT_BK;
+      const uint32_t sa = smem0 + (uint32_t)st * stage_bytes, sb = sa + a_bytes;
+      for (int idx = ptid; idx < LT_TM * CH; idx += NPROD) {
+        const int r = idx / CH, c = idx % CH;
+        const int gr = row0 + r, gk = k0 + c * 8;
+        const bool ok = (gr < p.M) && (gk < K);
+        cp_async16(sa + (uint32_t)(c * LT_TM + r) * 16u, p.x + (size_t)(ok ? gr : 0) * K + (ok ? gk : 0), ok ? 16 : 0);
+      }
+      for (int idx = ptid; idx < N * CH; idx += NPROD) {
+        const int r = idx / CH, c = idx % CH;
+        const int gk = k0 + c * 8;
+        const bool ok = gk < K;
+        cp_async16(sb + (uint32_t)(c * N + r) * 16u, p.w + (size_t)r * K + (ok ? gk : 0), ok ? 16 : 0);
+      }
+      // arrive on full[st] when all of THIS thread's copies above have landed
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * st) : "memory");
     }
-    for (int idx = tid; idx < N * (LT_BK / 8); idx += LT_THREADS) {
-      const int r = idx >> 3, c = idx & 7;
-      const int gk = k0 + c * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (gk < K) v = *reinterpret_cast<const uint4*>(p.w + (size_t)r * K + gk);
-      *reinterpret_cast<uint4*>(sB + ((size_t)c * N + r) * 16) = v;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
-    __syncthreads();
-    if (tid == 0) {
+  } else if (tid == 0) {
+    // ===== MMA ISSUER: one thread, tcgen05.mma back to back as stages fill =========================
+    const uint32_t idesc = make_instr_desc(N);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int st = kb % LT_STAGES;
+      mbar_wait(full0 + 8u * st, (uint32_t)((kb / LT_STAGES) & 1));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // LDGSTS (generic proxy) -> UMMA (async proxy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int rem = K - k0;
+      const int rem = K - kb * LT_BK;
       const int ksteps = (rem >= LT_BK) ? (LT_BK / 16) : ((rem + 15) / 16);
-      for (int s = 0; s < ksteps; ++s) {
-        const uint64_t da = make_smem_desc(smem_u32(sA) + (uint32_t)s * 2u * LT_TM * 16u, LT_TM * 16u, 128u);
-        const uint64_t db = make_smem_desc(smem_u32(sB) + (uint32_t)s * 2u * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
-        const uint32_t accum = (kb > 0 || s > 0) ? 1u : 0u;
+      const uint32_t sa = smem0 + (uint32_t)st * stage_bytes, sb = sa + a_bytes;
+      for (int s2 = 0; s2 < ksteps; ++s2) {
+        const uint64_t da = make_smem_desc(sa + (uint32_t)s2 * 2u * LT_TM * 16u, LT_TM * 16u, 128u);
+        const uint64_t db = make_smem_desc(sb + (uint32_t)s2 * 2u * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+        const uint32_t accum = (kb > 0 || s2 > 0) ? 1u : 0u;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
@@ -128,13 +154,15 @@ __global__ void __launch_bounds__(LT_THREADS) linear_tc_kernel(const LinearParam
             ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
             : "memory");
       }
-      // arrives on the mbarrier once every MMA issued so far has finished reading smem / writing TMEM
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a)
+      // free the slot for the producers once these MMAs have finished reading it
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8u * st)
                    : "memory");
     }
-    mbar_wait(bar_a, parity);
-    parity ^= 1u;
+    // accumulator complete (commits retire in issue order)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done_bar)
+                 : "memory");
   }
+  mbar_wait(done_bar, 0u);
   // ---- epilogue: TMEM -> registers -> bias + ReLU -> global -------------------------------------
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int row = row0 + warp * 32 + lane;                 // TMEM lane == tile row (M = 128)
@@ -152,16 +180,28 @@ __global__ void __launch_bounds__(LT_THREADS) linear_tc_kernel(const LinearParam
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (row < p.M) {
-      const int nvalid = min(32, N - cb);
+      // N % 16 == 0, so every group of 8 columns is entirely inside or outside the matrix:
+      // 16-byte (bf16) / 2 x 16-byte (fp32) vector stores, bias + ReLU fused here
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < nvalid) {
-          float v = __uint_as_float(r[j]) + (p.bias ? p.bias[cb + j] : 0.f);
-          if (p.relu) v = fmaxf(v, 0.f);
-          if (kOutBf16)
-            reinterpret_cast<__nv_bfloat16*>(p.y)[(size_t)row * N + cb + j] = __float2bfloat16_rn(v);
-          else
-            reinterpret_cast<float*>(p.y)[(size_t)row * N + cb + j] = v;
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const int c0 = cb + g8 * 8;
+        if (c0 >= N) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = __uint_as_float(r[g8 * 8 + j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+          if (p.relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (kOutBf16) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)row * N + c0) = u;
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (size_t)row * N + c0);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
     }
@@ -175,7 +215,7 @@ __global__ void __launch_bounds__(LT_THREADS) linear_tc_kernel(const LinearParam
 
 cudaError_t launch_linear_tc(const LinearParams& p, cudaStream_t s) {
   if (p.N % 16 != 0 || p.N < 16 || p.N > 256 || p.K % 8 != 0 || p.M < 1) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(LT_BK / 8) * LT_TM * 16 + (size_t)(LT_BK / 8) * p.N * 16 + 64;
+  const size_t smem = LT_STAGES * ((size_t)(LT_BK / 8) * LT_TM * 16 + (size_t)(LT_BK / 8) * p.N * 16) + 128;
   const int grid = (p.M + LT_TM - 1) / LT_TM;
   cudaError_t e;
   if (p.out_bf16) {
