@@ -109,7 +109,7 @@ def main():
         tr.train_step(*pool[i % len(pool)])
     torch.cuda.synchronize()
     barrier(env)
-    sampler = ClockSampler(dev.index or 0, 100).start() if env.rank == 0 else None
+    sampler = ClockSampler(dev.index or 0, 25).start() if env.rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(env)
     torch.cuda.synchronize()
