@@ -44,7 +44,8 @@ def parse():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
                    help="split step: pushes on a side stream overlapping forward/backward "
-                        "(auto = on for N >= 4: measured 1.89 vs 2.09 ms/step at N=8, 3.32 vs 3.20 at N=2)")
+                        "(auto = on for N >= 2: measured 2.65 vs 2.83 ms/step at N=2, 1.95 vs 2.22 at N=4, "
+                        "1.89 vs 2.09 at N=8)")
     p.add_argument("--no-channels-last", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--out", default="")
@@ -89,7 +90,7 @@ def main():
                  dtype=args.dtype, batch_size=gb, batch_mode="global", epochs=10 ** 6,
                  sync_mode="iter" if algo == "decent" else args.sync_mode,
                  horizon=args.horizon, topk_percent=args.topk,
-                 overlap_push=(args.overlap == "on") or (args.overlap == "auto" and N >= 4 and backend == "p2p"),
+                 overlap_push=(args.overlap == "on") or (args.overlap == "auto" and N >= 2 and backend == "p2p"),
                  channels_last=not args.no_channels_last, cuda_graph=not args.no_graph,
                  train_samples=n_train, test_samples=256, quiet=True, augment=True)
     src = synthetic_source("cifar10", n_train).pin()
