@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnPar
 // ===========================================================================================
 // SPLIT path (large tensors)
 // ===========================================================================================
-__global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const BnParams p) {
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnParams p) {
   __shared__ __align__(16) float smem[BN_RPP * 128];
   const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_stats_kernel(const BnParams
   finalize_stats(p, slice, tot);
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_fwd_apply_kernel(const BnParams p) {
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_apply_kernel(const BnParams p) {
   const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
