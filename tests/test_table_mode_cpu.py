@@ -7,7 +7,7 @@ from eventgrad_b200.parallel.arena import ParamArena
 
 
 def test_shadow_modules_fall_back_to_plain_layers_on_cpu():
-    m = build_model("lenet")
+    m = build_model("lenet").eval()          # eval: Dropout2d off, so two forwards are comparable
     assert isinstance(m.conv1, ShadowConv2d) and isinstance(m.fc1, ShadowLinear)
     x = torch.randn(2, 3, 32, 32)
     y1 = m(x)
