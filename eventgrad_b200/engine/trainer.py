@@ -223,6 +223,7 @@ class Trainer:
                     break
             # ---- epoch boundary: the only host syncs of the training loop ----------------
             acc = 100.0 * float(self.correct.item()) / max(1, self.sampler.local_size)
+            self._check_device_status()
             if not cfg.quiet:
                 if cfg.dataset == "mnist":
                     print(f"{self.epoch}, {acc:g}", flush=True)                       # event.cpp:498
@@ -242,6 +243,18 @@ class Trainer:
         self.train_time_s = time.perf_counter() - t0
         if env.rank == 0 and not cfg.quiet:
             print(f"Training time - {self.train_time_s:g}", flush=True)               # event.cpp:495-497
+
+    def _check_device_status(self) -> None:
+        """Raise if a device-side wait timed out (sticky status words of the fused kernels): a wedged
+        or dead peer shows up here as an exception instead of a hang (the reference would block
+        forever in MPI_Recv / silently average a frozen copy -- SURVEY.md section 5)."""
+        if hasattr(self.backend, "check_status"):
+            self.backend.check_status()
+        if self.device.type == "cuda":
+            from ..ops.bn_act import bn_status
+            st = bn_status(self.device)
+            if st != 0:
+                raise RuntimeError(f"fused BN kernels: device status {st} (flag wait timed out)")
 
     def finalize(self, evaluate: bool = True) -> dict:
         """Event statistics, final model averaging, rank-0 test (event.cpp:499-573)."""
