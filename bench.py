@@ -204,7 +204,14 @@ def main():
     events_all = sum_over_ranks(be.num_events(), env)
     dense_msgs = 2 * table.n_tensors * total_steps * N
     push_bytes_step = bytes_rank / max(1, total_steps)
-    kern_per_step = {"decent": 1, "event": 1, "cent": 1, "spevent": 11}[algo] + (1 if (cfg.overlap_push and algo in ("decent", "event") and N > 1) else 0)
+    # kernels of THIS repo launched per step inside the timed region: the exchange/update kernel(s) plus
+    # the fused BatchNorm kernels (2 forward + 2 backward per BN layer when the bf16 NHWC path is active)
+    from eventgrad_b200.ops.bn_act import FusedBNAct
+    n_bn = sum(1 for m in tr.model.modules() if isinstance(m, FusedBNAct))
+    bn_native = args.dtype == "bf16" and cfg.channels_last and os.environ.get("EGB_FUSED_BN", "1") != "0"
+    step_kernels = {"decent": 1, "event": 1, "cent": 1, "spevent": 11}[algo] \
+        + (1 if (cfg.overlap_push and algo in ("decent", "event") and N > 1) else 0)
+    kern_per_step = (step_kernels if args.impl == "ours" else 0) + (4 * n_bn if bn_native else 0)
     out = {
         "metric": "images/sec, CIFAR-10 ResNet (reference topology) D-PSGD ring gossip training step",
         "value": value, "unit": "images/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
@@ -213,7 +220,7 @@ def main():
         "impl": args.impl,
         "config": {"model": f"{args.model}-ref(12 BasicBlocks, 86 tensors, {table.n_elems} params)"
                             if args.model == "resnet18" else args.model,
-                   "global_batch": gb, "per_gpu_batch": per_rank, "image": "3x32x32",
+                   "global_batch": gb, "per_gpu_batch": per_rank, "seq_len": None, "image": "3x32x32",
                    "parallelism": f"dp{N}-ring-gossip" if algo != "cent" else f"dp{N}-allreduce",
                    "algorithm": args.algo, "backend": backend, "sync_mode": cfg.sync_mode, "overlap_push": cfg.overlap_push,
                    "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": cfg.cuda_graph,
@@ -221,8 +228,9 @@ def main():
                    "l2_policy": "per-step working set (theta,grad,mom,2 inboxes = "
                                 f"{5 * table.n_padded * 4 / 1e6:.0f} MB + activations) exceeds the 126 MB L2; "
                                 "no explicit flush"},
-        "gpu_launches": int(kern_per_step * args.steps) if args.impl == "ours" else 0,
-        "own_kernels_per_step": kern_per_step if args.impl == "ours" else 0,
+        "gpu_launches": int(kern_per_step * args.steps),
+        "own_kernels_per_step": {"exchange_update": step_kernels if args.impl == "ours" else 0,
+                                 "fused_batchnorm": 4 * n_bn if bn_native else 0},
         "comm": {"bytes_pushed_per_step_per_gpu": push_bytes_step,
                  "events_total": events_all, "dense_messages": dense_msgs,
                  "messages_saved": (1.0 - events_all / dense_msgs) if (algo in ("event", "spevent") and dense_msgs and N > 1) else 0.0,

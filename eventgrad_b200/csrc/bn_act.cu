@@ -8,7 +8,7 @@
 // memory-bound glue.
 //
 // Geometry.  NHWC == row-major [M = N*H*W, C].  The tensor is cut into C/64 channel SLICES; a CTA
-// works on one slice (blockIdx.y) and one row split (blockIdx.x): 8 threads x 8 channels (one
+// works on one slice (blockIdx.x, fastest) and one row split (blockIdx.y): 8 threads x 8 channels (one
 // 128-byte line) per row, 32 rows per pass.  Per-slice partial sums are combined in fixed order by
 // the last CTA *of that slice*, so the combine work is spread over C/64 CTAs and is tiny.
 //
@@ -169,7 +169,7 @@ __device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int
 // ===========================================================================================
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnParams p) {
   __shared__ __align__(16) float smem[BN_RPP * 128];
-  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(p.epoch);
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnPar
     publish_flag(p.flag + slice, epoch + 1u);
     if (threadIdx.x == 0) {                                 // global epoch bump by the last slice to finish
       const unsigned prev = atomicAdd(p.ticket + 63, 1u);
-      if (prev == gridDim.y - 1) {
+      if (prev == gridDim.x - 1) {
         p.ticket[63] = 0u;
         *p.epoch = epoch + 1u;
       }
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnPar
 // ===========================================================================================
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnParams p) {
   __shared__ __align__(16) float smem[BN_RPP * 128];
-  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(p.epoch);
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnPar
     publish_flag(p.flag + slice, epoch + 1u);
     if (threadIdx.x == 0) {
       const unsigned prev = atomicAdd(p.ticket + 63, 1u);
-      if (prev == gridDim.y - 1) {
+      if (prev == gridDim.x - 1) {
         p.ticket[63] = 0u;
         *p.epoch = epoch + 1u;
       }
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnPar
 // ===========================================================================================
 __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnParams p) {
   __shared__ __align__(16) float smem[BN_RPP * 128];
-  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
   float s[8], q[8];
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnPar
 }
 
 __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_apply_kernel(const BnParams p) {
-  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
   float sc[8], sh[8];
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_apply_kernel(const BnPar
 
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParams p) {
   __shared__ __align__(16) float smem[BN_RPP * 128];
-  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
   float mu[8], is[8], s1[8], s2[8];
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParam
 }
 
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_dx_kernel(const BnParams p) {
-  const int slice = blockIdx.y, rs = blockIdx.x, RS = gridDim.x;
+  const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
   float mu[8], is[8], k0[8], k1[8], k2[8];
@@ -514,19 +514,19 @@ cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s
     const long long cap = (long long)(8 * sm_count) / slices;
     if (rsn > cap) rsn = cap;
     if (rsn < 1) rsn = 1;
-    return dim3((unsigned)rsn, (unsigned)slices);
+    return dim3((unsigned)slices, (unsigned)rsn);
   };
   auto red_grid = [&]() {
     long long rsn = ceil_div(passes, 8);
     const long long cap = (long long)split_cap / slices;
     if (rsn > cap) rsn = cap;
     if (rsn < 1) rsn = 1;
-    return dim3((unsigned)rsn, (unsigned)slices);
+    return dim3((unsigned)slices, (unsigned)rsn);
   };
   if (which == 0) {
     const long long rs_f = ceil_div(passes, BN_FWD_PASSES);
     if (p.fused_ok && rs_f * slices <= max_ctas) {
-      bn_fwd_fused_kernel<<<dim3((unsigned)rs_f, (unsigned)slices), BN_THREADS, 0, s>>>(p);
+      bn_fwd_fused_kernel<<<dim3((unsigned)slices, (unsigned)rs_f), BN_THREADS, 0, s>>>(p);
     } else {
       bn_fwd_stats_kernel<<<red_grid(), BN_THREADS, 0, s>>>(p);
       bn_fwd_apply_kernel<<<map_grid(4), BN_THREADS, 0, s>>>(p);
@@ -536,7 +536,7 @@ cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s
   } else if (which == 2) {
     const long long rs_b = ceil_div(passes, BN_BWD_PASSES);
     if (p.fused_ok && rs_b * slices <= max_ctas) {
-      bn_bwd_fused_kernel<<<dim3((unsigned)rs_b, (unsigned)slices), BN_THREADS, 0, s>>>(p);
+      bn_bwd_fused_kernel<<<dim3((unsigned)slices, (unsigned)rs_b), BN_THREADS, 0, s>>>(p);
     } else {
       bn_bwd_reduce_kernel<<<red_grid(), BN_THREADS, 0, s>>>(p);
       bn_bwd_dx_kernel<<<map_grid(2), BN_THREADS, 0, s>>>(p);
