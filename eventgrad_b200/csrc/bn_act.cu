@@ -508,7 +508,7 @@ cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s
   const int slices = p.C / BN_SLICE;
   const long long passes = ceil_div(p.M, BN_RPP);
   const int max_ctas = 2 * sm_count;                       // co-residency bound of the fused kernels
-  const int split_cap = bn_partial_rows(sm_count) - 64;    // total CTAs of a split reduction
+  const int split_cap = 2 * sm_count;                      // reductions: ONE wave of fat CTAs (2 resident per SM)
   auto map_grid = [&](int rows_per_cta_passes) {
     long long rsn = ceil_div(passes, rows_per_cta_passes);
     const long long cap = (long long)(8 * sm_count) / slices;
