@@ -65,6 +65,8 @@ class TrainConfig:
     channels_last: bool = False
     cuda_graph: bool = False
     max_steps: int = 0               # >0: stop after this many steps (tests / bench)
+    cudnn_benchmark: bool = True     # cuDNN autotune: best steady state, but every new conv shape costs a
+                                     # one-time search (seconds; it also hits the partial last batch)
     host_threads: int = 2            # intra-op CPU threads on GPU runs (0 = leave torch's default)
     # ---- observability -------------------------------------------------------
     file_write: int = 0              # reference debug files send/recv/train/values<r>.txt
@@ -152,6 +154,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--dtype", default=None, choices=["fp32", "tf32", "bf16"])
     p.add_argument("--channels-last", action="store_true", default=None)
     p.add_argument("--cuda-graph", action="store_true", default=None)
+    p.add_argument("--no-cudnn-benchmark", dest="cudnn_benchmark", action="store_false", default=None)
     p.add_argument("--max-steps", type=int, default=None)
     p.add_argument("--log-dir", default=None)
     p.add_argument("--ckpt-dir", default=None)

@@ -46,7 +46,7 @@ class Trainer:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
         if dev.type == "cuda":
-            torch.backends.cudnn.benchmark = True
+            torch.backends.cudnn.benchmark = bool(cfg.cudnn_benchmark)
             if cfg.host_threads > 0:
                 # The host side of a GPU step is a 0.8 MB gather + a few launches.  A 64-thread OpenMP
                 # pool for that costs milliseconds per step (wake-ups contending with the thread that
