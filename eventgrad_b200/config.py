@@ -75,6 +75,7 @@ class TrainConfig:
     ckpt_every: int = 0              # epochs; 0 = never
     resume: str = ""
     quiet: bool = False
+    phase_timers: bool = False       # per-phase device timers (CUDA events + NVTX ranges), printed by rank 0
 
     def validate(self) -> "TrainConfig":
         if self.algo not in ALGOS:
@@ -161,6 +162,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--ckpt-every", type=int, default=None)
     p.add_argument("--resume", default=None)
     p.add_argument("--quiet", action="store_true", default=None)
+    p.add_argument("--phase-timers", action="store_true", default=None)
     del d
 
 

@@ -80,7 +80,7 @@ class Trainer:
                                   out_dtype=torch.float32, channels_last=cfg.channels_last,
                                   seed=cfg.seed)
         self.logw = RefLogWriter(cfg.log_dir, env.rank, cfg.algo, cfg.dataset, bool(cfg.file_write))
-        self.timer = PhaseTimer(dev, enabled=False)
+        self.timer = PhaseTimer(dev, enabled=bool(cfg.phase_timers))
         self.correct = torch.zeros((), dtype=torch.int64, device=dev)
         self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
         self.last_loss: Optional[torch.Tensor] = None
@@ -149,11 +149,14 @@ class Trainer:
 
     def _eager_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         if getattr(self.backend, "graph_safe", False):
-            loss = self._fwd_bwd_launch(x, y)
+            with self.timer.phase("step(fwd+bwd+fused_update)"):
+                loss = self._fwd_bwd_launch(x, y)
             self.backend.account_step()
         else:
-            loss = self._fwd_bwd(x, y)
-            self.backend.step()
+            with self.timer.phase("fwd_bwd"):
+                loss = self._fwd_bwd(x, y)
+            with self.timer.phase("comm_update"):
+                self.backend.step()
         return loss
 
     def _graphed_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -243,6 +246,11 @@ class Trainer:
         self.train_time_s = time.perf_counter() - t0
         if env.rank == 0 and not cfg.quiet:
             print(f"Training time - {self.train_time_s:g}", flush=True)               # event.cpp:495-497
+        if cfg.phase_timers:
+            ms = self.timer.summary_ms()
+            if env.rank == 0 and not cfg.quiet:
+                print("phase timers (ms/call): " + ", ".join(f"{k}={v:.3f}" for k, v in ms.items()), flush=True)
+            self.phase_ms = ms
 
     def _check_device_status(self) -> None:
         """Raise if a device-side wait timed out (sticky status words of the fused kernels): a wedged

@@ -24,7 +24,11 @@ class DistEnv:
     backend: str          # nccl | gloo | none
 
 
-def init_distributed(device_pref: str = "auto", timeout_s: int = 600) -> DistEnv:
+def init_distributed(device_pref: str = "auto", timeout_s: int = 0) -> DistEnv:
+    """timeout_s bounds every collective of the process group (0: $EGB_DIST_TIMEOUT or 600 s): a dead
+    rank surfaces as an exception on its peers instead of the reference's indefinite MPI_Recv hang."""
+    if timeout_s <= 0:
+        timeout_s = int(os.environ.get("EGB_DIST_TIMEOUT", "600"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))

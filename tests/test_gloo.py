@@ -53,3 +53,26 @@ def test_mnist_event_program_logs_and_counts(tmp_path):
     assert len(send) == 16                                          # ceil(1024/64) steps
     assert len(send[0].split(",  ")) == 8 * 3 + 1                   # norm, thres, fired per tensor
     assert os.path.exists(tmp_path / "recv1.txt")
+
+
+def test_dead_rank_is_detected_not_hung():
+    """in the reference a dead rank hangs `decent` forever (blocking MPI_Recv).
+    Here every collective is bounded: the survivor raises within the process-group timeout."""
+    import time
+    _PORT[0] += 1
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_PORT[0]), os.path.join(ROOT, "tests", "fail_worker.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="1", EGB_DIST_TIMEOUT="10")
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT, env=env)
+    out = r.stdout + r.stderr
+    assert "UNEXPECTED_COMPLETION" not in out
+    assert "PEER_FAILURE_DETECTED rank=0" in out or r.returncode != 0, out[-1500:]
+    assert time.time() - t0 < 150
+
+
+def test_phase_timers_cpu():
+    rc, out = _torchrun(2, ["-m", "eventgrad_b200.cli.decent"], "0", "--epochs", "2", "--train-samples", "512",
+                        "--test-samples", "128", "--device", "cpu", "--phase-timers")
+    assert rc == 0, out[-1500:]
+    assert "phase timers (ms/call): fwd_bwd=" in out and "comm_update=" in out
