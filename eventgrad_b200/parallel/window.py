@@ -89,7 +89,13 @@ class Window:
             for r, h in enumerate(handles):
                 if r == self.rank:
                     continue
-                p = self._C.ipc_open(h)
+                try:
+                    p = self._C.ipc_open(h)
+                except RuntimeError as e:
+                    raise RuntimeError(
+                        f"rank {self.rank}: cannot map the window of rank {r} ({e}). The p2p backend needs "
+                        "CUDA IPC + peer access between all GPUs of the node (NVLink/NVSwitch or PCIe P2P, one "
+                        "process per GPU in the same IPC namespace); use --backend nccl otherwise.") from e
                 self.peer_ptrs[r] = p
                 self._opened.append(p)
 
