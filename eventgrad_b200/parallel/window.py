@@ -19,10 +19,6 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-_DT = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.int64: "<i8",
-       torch.bfloat16: None}
-
-
 class _RawCuda:
     """Minimal __cuda_array_interface__ holder so torch can alias raw device memory."""
 

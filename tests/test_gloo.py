@@ -74,3 +74,26 @@ def test_phase_timers_cpu():
                         "--test-samples", "128", "--device", "cpu", "--phase-timers")
     assert rc == 0, out[-1500:]
     assert "phase timers (ms/call): fwd_bwd=" in out and "comm_update=" in out
+
+
+def test_all_five_programs_run_on_the_plumbing_backend(tmp_path):
+    """decent / cifar_event / cifar_spevent end to end on CPU+gloo (cent and mnist_event have their own
+    tests above): output contract of SURVEY.md A.3 and the message accounting."""
+    import json
+    import re
+    rc, out = _torchrun(3, ["-m", "eventgrad_b200.cli.decent"], "1", "--epochs", "3", "--train-samples", "900",
+                        "--test-samples", "200", "--device", "cpu", "--log-dir", str(tmp_path))
+    assert rc == 0 and "Training time - " in out and "Test Accuracy - " in out, out[-1500:]
+    assert len(open(tmp_path / "values1.txt").read().splitlines()) == 3            # "<epoch>, <loss>"
+    rc, out = _torchrun(2, ["-m", "eventgrad_b200.cli.cifar_event"], "1", "1", "0.9", "--model", "lenet", "--epochs",
+                        "2", "--train-samples", "1024", "--test-samples", "200", "--device", "cpu", "--log-dir",
+                        str(tmp_path))
+    assert rc == 0 and out.count("Accuracy in epoch") >= 4 and "Total number of events - " in out, out[-1500:]
+    n_steps = 2 * 4                                                                # 512 per rank / batch 128
+    assert len(open(tmp_path / "train0.txt").read().splitlines()) == n_steps       # "<pass_num>, <loss>"
+    assert len(open(tmp_path / "send1.txt").read().splitlines()) == n_steps
+    summ = json.loads(re.search(r"summary (\{.*\})", out).group(1))
+    assert summ["dense_messages"] == 2 * 10 * n_steps * 2 and 0 < summ["events_total"] <= summ["dense_messages"]
+    rc, out = _torchrun(3, ["-m", "eventgrad_b200.cli.cifar_spevent"], "0", "1", "1.0", "5", "--model", "lenet",
+                        "--epochs", "1", "--train-samples", "1536", "--test-samples", "200", "--device", "cpu")
+    assert rc == 0 and "Number of topk elements - 3103" in out and out.count("No of events in rank") == 3, out[-1500:]
