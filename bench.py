@@ -69,7 +69,6 @@ def main():
         return reference_arm(args)
 
     import torch
-    import torch.nn.functional as F
     from eventgrad_b200.config import preset
     from eventgrad_b200.data import synthetic_source
     from eventgrad_b200.engine.trainer import Trainer

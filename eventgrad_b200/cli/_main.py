@@ -2,7 +2,6 @@
 from __future__ import annotations
 
 import json
-import sys
 from typing import Optional, Sequence
 
 from ..config import parse_cli

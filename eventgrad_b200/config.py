@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import argparse
 import dataclasses
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Sequence
 
 ALGOS = ("cent", "decent", "event", "spevent")

@@ -7,7 +7,7 @@ batch k+1 overlaps the training step of batch k.
 """
 from __future__ import annotations
 
-from typing import Iterator, Optional, Tuple
+from typing import Iterator, Tuple
 
 import torch
 

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..ops.shadow import ShadowConv2d, ShadowLinear
+from ..ops.shadow import ShadowLinear
 
 
 class MLP(nn.Module):

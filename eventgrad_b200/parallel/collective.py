@@ -19,7 +19,7 @@ on gloo it doubles as the GPU-free plumbing for BASELINE config 1.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,7 @@ No NCCL/MPI call, no separate elementwise kernel and no host synchronisation on 
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 

@@ -15,7 +15,7 @@ p2p backend) and the trainer drains them at epoch boundaries.
 from __future__ import annotations
 
 import os
-from typing import Iterable, Optional
+from typing import Iterable
 
 from ..parallel.base import StepLog
 

@@ -6,7 +6,7 @@ from eventgrad_b200.config import parse_cli, preset
 from eventgrad_b200.data import synthetic_source
 from eventgrad_b200.engine.trainer import Trainer
 from eventgrad_b200.parallel.topology import Ring
-from eventgrad_b200.utils.ckpt import ckpt_path, load_checkpoint, save_checkpoint
+from eventgrad_b200.utils.ckpt import ckpt_path
 from eventgrad_b200.utils.dist import DistEnv
 
 

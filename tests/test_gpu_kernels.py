@@ -4,8 +4,6 @@ Multi-rank behaviour is exercised on ONE GPU through ops.local_world.LocalWorld:
 ranks (own window / arena / stream each) whose kernels really handshake through flags in
 device memory.  Golden model: engine.simulator.RingSimulator.
 """
-import math
-
 import pytest
 import torch
 
