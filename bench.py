@@ -32,7 +32,9 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refport"],
+                   help="ours: fused p2p kernels | nccl: batched torch.distributed baseline | refport: reference-"
+                        "structured per-tensor port (host sync per tensor) | reference: the unmodified reference (unavailable)")
     p.add_argument("--algo", default="dpsgd", choices=["dpsgd", "event", "spevent", "cent"])
     p.add_argument("--model", default="resnet18")
     p.add_argument("--global-batch", type=int, default=256)
@@ -82,7 +84,7 @@ def main():
     gb = args.global_batch if args.scaling == "strong" else args.global_batch * N
     per_rank = max(1, gb // N)
     algo = {"dpsgd": "decent", "event": "event", "spevent": "spevent", "cent": "cent"}[args.algo]
-    backend = "p2p" if args.impl == "ours" else "nccl"
+    backend = {"ours": "p2p", "nccl": "nccl", "refport": "refport"}[args.impl]
     steps_needed = args.warmup + args.steps + 2
     n_train = max(per_rank * N * 8, 4096)
     cfg = preset("cifar_event", algo=algo, model=args.model, backend=backend, device="cuda",

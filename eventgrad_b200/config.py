@@ -45,7 +45,7 @@ class TrainConfig:
     initial_comm_passes: int = 30
     topk_percent: float = 10.0       # spevent only
     # ---- communication ---------------------------------------------------
-    backend: str = "auto"            # auto | p2p (fused sm_100a kernels) | nccl | gloo
+    backend: str = "auto"            # auto | p2p (fused sm_100a kernels) | nccl | gloo | refport (reference-structured)
     sync_mode: str = "iter"          # iter (deterministic handshake) | async (reference RMA semantics)
     final_divide_all: bool = True    # reference divides on rank 0 only (Q5)
     grad_table: bool = True          # p2p gossip: step kernel reads autograd's gradients in place (+ bf16
@@ -142,7 +142,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--seed", type=int, default=None)
     p.add_argument("--sent-history", type=int, default=None)
     p.add_argument("--initial-comm-passes", type=int, default=None)
-    p.add_argument("--backend", default=None, choices=["auto", "p2p", "nccl", "gloo"])
+    p.add_argument("--backend", default=None, choices=["auto", "p2p", "nccl", "gloo", "refport"])
     p.add_argument("--sync-mode", default=None, choices=["iter", "async"])
     p.add_argument("--overlap-push", action="store_true", default=None)
     p.add_argument("--no-grad-table", dest="grad_table", action="store_false", default=None)

@@ -12,5 +12,8 @@ def make_backend(cfg, arena, ring, env, group=None):
     if name == "p2p":
         from .p2p import P2PBackend
         return P2PBackend(cfg, arena, ring, env, group)
+    if name == "refport":
+        from .refstyle import ReferenceStyleBackend
+        return ReferenceStyleBackend(cfg, arena, ring, group)
     from .collective import CollectiveBackend
     return CollectiveBackend(cfg, arena, ring, group)

@@ -37,7 +37,7 @@ def main():
     ap.add_argument("--sync-mode", default="iter")
     ap.add_argument("--overlap", action="store_true")
     a = ap.parse_args()
-    dev_pref = "cpu" if a.backend == "gloo" else "cuda"
+    dev_pref = "cpu" if (a.backend == "gloo" or os.environ.get("EGB_WORKER_CPU") == "1") else "cuda"
     env = init_distributed(dev_pref)
     cfg = TrainConfig(algo=a.algo, dataset=a.dataset, model=a.model, lr=0.05, momentum=a.momentum,
                       horizon=a.horizon, thres_type=a.thres_type, constant=a.constant,

@@ -97,3 +97,16 @@ def test_all_five_programs_run_on_the_plumbing_backend(tmp_path):
     rc, out = _torchrun(3, ["-m", "eventgrad_b200.cli.cifar_spevent"], "0", "1", "1.0", "5", "--model", "lenet",
                         "--epochs", "1", "--train-samples", "1536", "--test-samples", "200", "--device", "cpu")
     assert rc == 0 and "Number of topk elements - 3103" in out and out.count("No of events in rank") == 3, out[-1500:]
+
+
+@pytest.mark.parametrize("algo", ["cent", "decent", "event"])
+def test_reference_structured_backend_matches_simulator(algo):
+    """parallel/refstyle.py (per-tensor host loop with .item() syncs, the shape of the reference's main())
+    must produce exactly what the simulator / the batched backends produce."""
+    _PORT[0] += 1
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr",
+           "127.0.0.1", "--master-port", str(_PORT[0]), os.path.join(ROOT, "tests", "dist_worker.py"), "--algo", algo,
+           "--backend", "refport", "--steps", "8"]
+    env = dict(os.environ, OMP_NUM_THREADS="1", EGB_WORKER_CPU="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and "WORKER_OK" in r.stdout + r.stderr, (r.stdout + r.stderr)[-2000:]
