@@ -22,7 +22,7 @@ NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPI
                            "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 CU_SOURCES = ["gossip.cu", "allreduce.cu", "sparse.cu", "augment.cu", "ipc.cu", "bn_act.cu", "linear_tc.cu"]
 CPP_SOURCES = ["bindings.cpp"]
-HEADERS = ["api.h", "common.cuh"]
+HEADERS = ["api.h", "common.cuh", "host_loader.h"]
 
 
 def so_path() -> str:
@@ -88,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         link = ["g++", "-shared", "-o", out] + objs
         for d in rdirs:
             link += ["-L", d, f"-Wl,-rpath,{d}"]
-        link += ["-l:libcudart.so.12"]
+        link += ["-l:libcudart.so.12", "-lpthread"]
         _run(link, log)
     with open(os.path.join(BUILD, "build.log"), "w") as f:
         f.write("\n".join(log))

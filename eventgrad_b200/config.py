@@ -56,6 +56,7 @@ class TrainConfig:
     data: str = "synthetic"          # synthetic | path to dataset root
     sampler: str = "random"          # random | sequential
     augment: bool = True             # pad4 + flip + crop (cifar only)
+    native_loader: str = "auto"      # auto (CPU: native C++ prefetcher, CUDA: Python staging) | on | off
     train_samples: int = 50000
     test_samples: int = 10000
     test_batch_size: int = 100
@@ -149,6 +150,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--data", default=None, help="'synthetic' or dataset root directory")
     p.add_argument("--sampler", default=None, choices=["random", "sequential"])
     p.add_argument("--no-augment", dest="augment", action="store_false", default=None)
+    p.add_argument("--native-loader", default=None, choices=["auto", "on", "off"])
     p.add_argument("--train-samples", type=int, default=None)
     p.add_argument("--test-samples", type=int, default=None)
     p.add_argument("--device", default=None, choices=["auto", "cuda", "cpu"])

@@ -11,6 +11,7 @@
 #include <unordered_map>
 
 #include "api.h"
+#include "host_loader.h"
 
 namespace py = pybind11;
 using namespace egb;
@@ -229,6 +230,34 @@ PYBIND11_MODULE(_C, m) {
                                       inv_std, out_bf16, nhwc, S(s)),
                 "decode_augment");
         });
+
+  // ---- native host-side batch prefetcher (data/native_loader.py) --------------------------------
+  py::class_<HostPrefetcher>(m, "HostPrefetcher")
+      .def(py::init([](uintptr_t images, uintptr_t labels, int64_t n, int64_t sample_bytes, int64_t batch,
+                       std::vector<uintptr_t> slot_images, std::vector<uintptr_t> slot_labels) {
+        if (slot_images.size() != slot_labels.size() || slot_images.empty())
+          throw std::invalid_argument("need the same positive number of image and label slots");
+        std::vector<uint8_t*> si;
+        std::vector<int64_t*> sl;
+        for (auto p : slot_images) si.push_back(reinterpret_cast<uint8_t*>(p));
+        for (auto p : slot_labels) sl.push_back(reinterpret_cast<int64_t*>(p));
+        return new HostPrefetcher(reinterpret_cast<const uint8_t*>(images), reinterpret_cast<const int64_t*>(labels), n,
+                                  sample_bytes, batch, std::move(si), std::move(sl));
+      }))
+      .def("start_epoch", [](HostPrefetcher& h, uintptr_t order, int64_t n_order) {
+        h.start_epoch(reinterpret_cast<const int64_t*>(order), n_order);
+      })
+      .def("num_batches", &HostPrefetcher::num_batches)
+      .def("next", [](HostPrefetcher& h) {
+        std::pair<int, int64_t> r;
+        {
+          py::gil_scoped_release nogil;      // the worker thread never needs the GIL; do not hold it while waiting
+          r = h.next();
+        }
+        return py::make_tuple(r.first, r.second);
+      })
+      .def("release", &HostPrefetcher::release)
+      .def("stop", &HostPrefetcher::stop);
 
   // ---- IPC window runtime -------------------------------------------------------------------
   m.def("ipc_alloc", [](size_t nbytes) {

@@ -19,7 +19,7 @@ from .sources import DataSource
 class BatchLoader:
     def __init__(self, source: DataSource, sampler: ShardSampler, batch: int, device,
                  augment: bool = False, out_dtype: torch.dtype = torch.float32,
-                 channels_last: bool = False, seed: int = 0, prefetch: bool = True):
+                 channels_last: bool = False, seed: int = 0, prefetch: bool = True, native: str = "auto"):
         self.src, self.sampler, self.batch = source, sampler, batch
         self.device = torch.device(device)
         self.augment, self.out_dtype, self.channels_last = augment, out_dtype, channels_last
@@ -35,6 +35,17 @@ class BatchLoader:
                 self._stage.append((xi, yi))
             self.copy_stream = torch.cuda.Stream(device=self.device)
         self.h2d_bytes_per_batch = batch * (c * h * w + 8)
+        # native host prefetcher (C++ worker thread, csrc/host_loader.h): default on the CPU path, opt-in
+        # ("on") on the CUDA path until it has been validated on hardware
+        self.native = None
+        want_native = (native == "on") or (native == "auto" and not self.cuda)
+        if want_native:
+            from .native_loader import NativeHostBatches, native_available
+            if native_available():
+                try:
+                    self.native = NativeHostBatches(source, batch, n_slots=4, pinned=self.cuda)
+                except TypeError:
+                    self.native = None
 
     def __len__(self) -> int:
         return self.sampler.num_batches(self.batch)
@@ -67,10 +78,19 @@ class BatchLoader:
         order = self.sampler.indices()
         nb = len(self)
         if not self.cuda:
+            if self.native is not None:
+                for xs, ys, slot in self.native.batches(order):
+                    x, y = self._decode(xs), ys.clone()
+                    self.native.release(slot)
+                    yield x, y
+                return
             for b in range(nb):
                 idx = order[b * self.batch:(b + 1) * self.batch]
                 x, y = self._host_batch(idx, 0)
                 yield self._decode(x), y
+            return
+        if self.native is not None:
+            yield from self._iter_cuda_native(order)
             return
         cur = torch.cuda.current_stream(self.device)
         pending = None
@@ -101,6 +121,31 @@ class BatchLoader:
             yield x, yd
             if not self.prefetch and b + 1 < nb:
                 pending = issue(b + 1)
+
+
+    def _iter_cuda_native(self, order):
+        """CUDA path fed by the native prefetcher: the worker stages batches into pinned slots ahead of
+        time; here only the async H2D + decode are issued.  A slot is handed back once its copy has run."""
+        cur = torch.cuda.current_stream(self.device)
+        inflight = []                                         # (slot, event) of issued H2D copies
+        for xs, ys, slot in self.native.batches(order):
+            with torch.cuda.stream(self.copy_stream):
+                xd = xs.to(self.device, non_blocking=True)
+                yd = ys.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            inflight.append((slot, ev))
+            while len(inflight) > 2:                          # keep <= 2 copies pending, recycle older slots
+                s0, e0 = inflight.pop(0)
+                e0.synchronize()
+                self.native.release(s0)
+            cur.wait_event(ev)
+            xd.record_stream(cur)
+            yd.record_stream(cur)
+            yield self._decode(xd), yd
+        for s0, e0 in inflight:
+            e0.synchronize()
+            self.native.release(s0)
 
 
 def eval_batches(source: DataSource, batch: int, device, out_dtype=torch.float32,

@@ -78,7 +78,7 @@ class Trainer:
         self.loader = BatchLoader(self.train_src, self.sampler, self.batch, dev,
                                   augment=cfg.augment and cfg.dataset == "cifar10",
                                   out_dtype=torch.float32, channels_last=cfg.channels_last,
-                                  seed=cfg.seed)
+                                  seed=cfg.seed, native=cfg.native_loader)
         self.logw = RefLogWriter(cfg.log_dir, env.rank, cfg.algo, cfg.dataset, bool(cfg.file_write))
         self.timer = PhaseTimer(dev, enabled=bool(cfg.phase_timers))
         self.correct = torch.zeros((), dtype=torch.int64, device=dev)
