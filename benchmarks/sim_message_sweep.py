@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--horizons", default="1.0,0.9")
+    ap.add_argument("--algo", default="event", choices=["event", "spevent"])
+    ap.add_argument("--topk", type=float, default=10.0)
+    ap.add_argument("--sampler", default="sequential", choices=["sequential", "random"])
+    ap.add_argument("--max-steps", type=int, default=0)
     ap.add_argument("--train-samples", type=int, default=60000)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -49,9 +53,9 @@ def main():
         arena = ParamArena(model)
         t = arena.table
         names = [n for n, _ in model.named_parameters()]
-        sim = RingSimulator(R, arena.theta.clone(), t, "event", TriggerConfig(1, hz, 0.0, 2, 30), lr=a.lr,
-                            momentum=a.momentum, serial_skip=False)
-        samplers = [ShardSampler(len(src), R, r, "sequential") for r in range(R)]
+        sim = RingSimulator(R, arena.theta.clone(), t, a.algo, TriggerConfig(1, hz, 0.0, 2, 30), lr=a.lr,
+                            momentum=a.momentum, topk_percent=a.topk, serial_skip=False)
+        samplers = [ShardSampler(len(src), R, r, a.sampler) for r in range(R)]
         steps_per_epoch = samplers[0].num_batches(a.batch)
         t0 = time.perf_counter()
         model.train()
@@ -69,6 +73,10 @@ def main():
                     g, = torch.autograd.grad(loss, th)
                     grads.append(g)
                 sim.step(grads)
+                if a.max_steps and sim.pass_num >= a.max_steps:
+                    break
+            if a.max_steps and sim.pass_num >= a.max_steps:
+                break
         # evaluate the averaged model
         avg = sim.final_average()
         model.eval()
@@ -76,7 +84,8 @@ def main():
             params = {n: avg[t.offsets[i]: t.offsets[i] + t.numels[i]].view(t.shapes[i]) for i, n in enumerate(names)}
             xt = decode_augment_torch(test.images, test.scale, test.mean, test.std)
             acc = 100.0 * float((functional_call(model, params, (xt,)).argmax(1) == test.labels).float().mean())
-        row = {"oracle": "RingSimulator (CPU)", "model": a.model, "world": R, "horizon": hz, "epochs": a.epochs,
+        row = {"oracle": "RingSimulator (CPU)", "model": a.model, "algo": a.algo,
+               "topk_percent": a.topk if a.algo == "spevent" else None, "world": R, "horizon": hz, "epochs": a.epochs,
                "steps": sim.pass_num, "events_total": sim.total_events(), "dense_messages": sim.dense_messages(),
                "messages_saved": 1.0 - sim.total_events() / sim.dense_messages(), "bytes_sent_all_ranks": int(sum(sim.bytes)),
                "test_acc": acc, "wall_s": time.perf_counter() - t0}
