@@ -99,3 +99,60 @@ def test_mutant_without_ack_is_caught():
         assert status == "ok"
         caught += bool(viol)
     assert caught > 0
+
+
+def run_double_buffered(R, G, n_tiles, n_warps, steps, depth, seed, max_ticks=400000):
+    """NEXT_STEPS.md item 2: dense gossip (every slice fires every step) with TWO inbox slots
+    (slot = step & 1) and NO ack at all."""
+    rng = random.Random(seed)
+    inbox = [{side: [[[0, 0] for _ in range(n_warps)] for _ in range(n_tiles)] for side in "lr"} for _ in range(R)]
+    flag = [{side: [[0] * n_warps for _ in range(n_tiles)] for side in "lr"} for _ in range(R)]
+    violations = []
+    iters = -(-n_tiles // G)
+
+    def warp(r, b, w):
+        L, Rn = (r - 1) % R, (r + 1) % R
+        for k in range(1, steps + 1):
+            for j in range(iters + depth):
+                t = b + j * G
+                if j < iters and t < n_tiles:
+                    inbox[L]["r"][t][w][k & 1] = k
+                    inbox[Rn]["l"][t][w][k & 1] = k
+                    yield None
+                    flag[L]["r"][t][w] = k
+                    flag[Rn]["l"][t][w] = k
+                    yield None
+                t2 = b + (j - depth) * G
+                if j >= depth and t2 < n_tiles:
+                    yield lambda t2=t2: flag[r]["l"][t2][w] >= k and flag[r]["r"][t2][w] >= k
+                    for side in "lr":
+                        got = inbox[r][side][t2][w][k & 1]
+                        if got != k:
+                            violations.append((r, side, t2, w, k, got))
+                    yield None
+
+    actors = [warp(r, b, w) for r in range(R) for b in range(G) for w in range(n_warps)]
+    pending = [next(a) for a in actors]
+    alive = set(range(len(actors)))
+    ticks = 0
+    while alive and ticks < max_ticks:
+        ready = [i for i in alive if pending[i] is None or pending[i]()]
+        if not ready:
+            return "deadlock", violations
+        i = rng.choice(ready)
+        try:
+            pending[i] = next(actors[i])
+        except StopIteration:
+            alive.discard(i)
+        ticks += 1
+    return ("ok" if not alive else "timeout"), violations
+
+
+@pytest.mark.parametrize("R,G,n_tiles,n_warps,depth", [(2, 2, 5, 2, 2), (3, 2, 5, 2, 2), (4, 2, 6, 2, 1), (5, 1, 4, 2, 3)])
+def test_ack_free_double_buffered_dense_gossip_design(R, G, n_tiles, n_warps, depth):
+    """Design check for the next round: with slot = step & 1 a sender can be at most one step ahead of a
+    receiver's reads (it needs the receiver's flags of step k+1 to finish k+1), so no ack is required."""
+    for seed in range(40):
+        status, viol = run_double_buffered(R, G, n_tiles, n_warps, steps=5, depth=depth, seed=seed)
+        assert status == "ok", (status, seed)
+        assert not viol, viol[:3]
