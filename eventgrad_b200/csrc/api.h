@@ -223,6 +223,8 @@ struct LinearParams {
   int out_bf16;
 };
 cudaError_t launch_linear_tc(const LinearParams& p, cudaStream_t s);
+// EXPERIMENTAL (not yet run on hardware): TMA + SWIZZLE_128B + persistent CTAs, csrc/linear_tc_tma.cu
+cudaError_t launch_linear_tc_tma(const LinearParams& p, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------ IPC window runtime
 // The RMA-window replacement (MPI_Alloc_mem + MPI_Win_create, event.cpp:138-147).

@@ -221,6 +221,16 @@ PYBIND11_MODULE(_C, m) {
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.out_bf16 = out_bf16;
     check(launch_linear_tc(p, S(s)), "linear_tc");
   });
+  m.def("linear_tc_tma", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int M, int N, int K, int relu,
+                            int out_bf16, int sm_count, uintptr_t s) {
+    LinearParams p;
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+    p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+    p.bias = reinterpret_cast<const float*>(bias);
+    p.y = reinterpret_cast<void*>(y);
+    p.M = M; p.N = N; p.K = K; p.relu = relu; p.out_bf16 = out_bf16;
+    check(launch_linear_tc_tma(p, sm_count, S(s)), "linear_tc_tma (experimental)");
+  });
   m.def("decode_augment",
         [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,
            int pad, float scale, float mean, float inv_std, int out_bf16, int nhwc, uintptr_t s) {

@@ -34,9 +34,15 @@ def linear_tc_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
     N = wb.shape[0]
     y = torch.empty(M, N, dtype=out_dtype, device=x.device)
     with torch.cuda.device(x.device):
-        ext().linear_tc(xb.data_ptr(), wb.data_ptr(), 0 if bf is None else bf.data_ptr(), y.data_ptr(), M, N, K,
-                        1 if relu else 0, 1 if out_dtype == torch.bfloat16 else 0,
-                        torch.cuda.current_stream(x.device).cuda_stream)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        if os.environ.get("EGB_TC_LINEAR") == "tma":
+            # experimental TMA / SWIZZLE_128B / persistent variant (csrc/linear_tc_tma.cu): opt-in only
+            sm = torch.cuda.get_device_properties(x.device).multi_processor_count
+            ext().linear_tc_tma(xb.data_ptr(), wb.data_ptr(), 0 if bf is None else bf.data_ptr(), y.data_ptr(), M, N, K,
+                                1 if relu else 0, 1 if out_dtype == torch.bfloat16 else 0, sm, stream)
+        else:
+            ext().linear_tc(xb.data_ptr(), wb.data_ptr(), 0 if bf is None else bf.data_ptr(), y.data_ptr(), M, N, K,
+                            1 if relu else 0, 1 if out_dtype == torch.bfloat16 else 0, stream)
     return y
 
 
