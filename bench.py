@@ -77,6 +77,9 @@ def main():
     from eventgrad_b200.utils.clocks import ClockSampler
     from eventgrad_b200.utils.dist import barrier, init_distributed, max_over_ranks, shutdown, sum_over_ranks
 
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "error": "bench.py needs a CUDA device (run it through gpurun / on the B200 box)"}))
+        return 2
     env = init_distributed("cuda")
     N = env.world
     if N != args.gpus and env.rank == 0:
