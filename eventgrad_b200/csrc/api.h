@@ -211,6 +211,15 @@ int bn_partial_rows(int sm_count);
 // which: 0 training forward, 1 apply only (eval), 2 backward
 cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s);
 
+// v2 (experimental, csrc/bn_act_v2.cu): the training forward also emits one ReLU bit per element and the
+// backward reads that mask instead of y.  mask: [C/64][M][8] bytes, required when relu != 0.
+struct BnParamsV2 {
+  BnParams b;
+  unsigned char* mask;
+};
+// which: 0 training forward, 2 backward
+cudaError_t launch_bn_v2(const BnParamsV2& p, int which, int sm_count, cudaStream_t s);
+
 // ------------------------------------------------------------------ tcgen05 fused Linear(+bias)(+ReLU)
 // Y[M,N] = act(X[M,K] * W[N,K]^T + b): bf16 operands, fp32 accumulation in TMEM (csrc/linear_tc.cu).
 struct LinearParams {

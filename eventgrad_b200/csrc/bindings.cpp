@@ -211,6 +211,54 @@ PYBIND11_MODULE(_C, m) {
     p.M = M; p.C = C; p.relu = relu; p.fused_ok = fused_ok;
     check(launch_bn(p, 2, sm_count, S(s)), "bn_backward");
   });
+  // experimental v2 (ReLU bit mask): same positional layout + the mask address
+  m.def("bn_forward_v2", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, uintptr_t gamma, uintptr_t beta,
+                            uintptr_t mean, uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt,
+                            uintptr_t partial, uintptr_t ticket, uintptr_t status, long long M, int C, float eps,
+                            float momentum, int relu, int sm_count, uintptr_t s) {
+    BnParamsV2 pp;
+    std::memset(&pp, 0, sizeof(pp));
+    BnParams& p = pp.b;
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+    p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    pp.mask = reinterpret_cast<unsigned char*>(mask);
+    p.gamma = reinterpret_cast<const float*>(gamma);
+    p.beta = reinterpret_cast<const float*>(beta);
+    p.mean = reinterpret_cast<float*>(mean);
+    p.invstd = reinterpret_cast<float*>(invstd);
+    p.run_mean = reinterpret_cast<float*>(run_mean);
+    p.run_var = reinterpret_cast<float*>(run_var);
+    p.nbt = reinterpret_cast<long long*>(nbt);
+    p.partial = reinterpret_cast<float*>(partial);
+    p.ticket = reinterpret_cast<unsigned int*>(ticket);
+    p.status = reinterpret_cast<int*>(status);
+    p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu;
+    check(launch_bn_v2(pp, 0, sm_count, S(s)), "bn_forward_v2");
+  });
+  m.def("bn_backward_v2", [](uintptr_t x, uintptr_t mask, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
+                             uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
+                             uintptr_t ticket, uintptr_t status, long long M, int C, int relu, int sm_count,
+                             uintptr_t s) {
+    BnParamsV2 pp;
+    std::memset(&pp, 0, sizeof(pp));
+    BnParams& p = pp.b;
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+    pp.mask = reinterpret_cast<unsigned char*>(mask);
+    p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+    p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
+    p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
+    p.gamma = reinterpret_cast<const float*>(gamma);
+    p.mean = reinterpret_cast<float*>(mean);
+    p.invstd = reinterpret_cast<float*>(invstd);
+    p.dgamma = reinterpret_cast<float*>(dgamma);
+    p.dbeta = reinterpret_cast<float*>(dbeta);
+    p.partial = reinterpret_cast<float*>(partial);
+    p.ticket = reinterpret_cast<unsigned int*>(ticket);
+    p.status = reinterpret_cast<int*>(status);
+    p.M = M; p.C = C; p.relu = relu;
+    check(launch_bn_v2(pp, 2, sm_count, S(s)), "bn_backward_v2");
+  });
   m.def("linear_tc", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int M, int N, int K, int relu,
                         int out_bf16, uintptr_t s) {
     LinearParams p;

@@ -35,7 +35,10 @@ def _workspace(device):
               "status": ctl[256:].data_ptr(), "C": C,
               # single-launch (spin-flag) variant for small tensors: measured SLOWER than the two-launch
               # split path inside a CUDA graph (1.52 vs 1.42 ms/step at batch 32), so it is opt-in
-              "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0}
+              "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0,
+              # EXPERIMENTAL csrc/bn_act_v2.cu (ReLU bit mask instead of re-reading y in the backward);
+              # opt-in until it has been validated on hardware (tests/test_gpu_experimental.py)
+              "v2": os.environ.get("EGB_BN_V2", "0") == "1"}
         _WS[device] = ws
     return ws
 
@@ -75,6 +78,18 @@ class _FusedBNActFn(torch.autograd.Function):
             invstd = torch.rsqrt(running_var + eps)
             rm = rv = nb = 0
         stream = torch.cuda.current_stream(x.device).cuda_stream
+        ctx.v2 = bool(ws["v2"] and training)
+        if ctx.v2:
+            mask = torch.empty(M * C // 8 if relu else 0, dtype=torch.uint8, device=x.device)
+            with torch.cuda.device(x.device):
+                C_ext.bn_forward_v2(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
+                                    mask.data_ptr() if relu else 0, weight.data_ptr(), bias.data_ptr(),
+                                    mean.data_ptr(), invstd.data_ptr(), rm, rv, nb, ws["partial"].data_ptr(),
+                                    ws["f"][0], ws["status"], M, C, float(eps), float(momentum),
+                                    1 if relu else 0, ws["sm"], stream)
+            ctx.save_for_backward(x, mask, weight, mean, invstd)
+            ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
+            return y
         with torch.cuda.device(x.device):
             C_ext.bn_forward(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
                              weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm, rv, nb,
@@ -101,6 +116,14 @@ class _FusedBNActFn(torch.autograd.Function):
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
+        if ctx.v2:                                    # `y` is the bit mask here
+            with torch.cuda.device(x.device):
+                C_ext.bn_backward_v2(x.data_ptr(), y.data_ptr() if ctx.relu else 0, dy.data_ptr(), dx.data_ptr(),
+                                     dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
+                                     invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                     ws["partial"].data_ptr(), ws["b"][0], ws["status"], M, C,
+                                     1 if ctx.relu else 0, ws["sm"], stream)
+            return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
         with torch.cuda.device(x.device):
             C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                               dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),

@@ -54,3 +54,76 @@ def test_p2p_file_write_logs(tmp_path):
     recv = open(tmp_path / "recv0.txt").read().splitlines()
     assert len(send) == 10 and len(recv) == 10 and len(send[0].split(",  ")) == 8 * 3 + 1
     tr.close()
+
+
+@pytest.fixture
+def bn_v2(monkeypatch):
+    """Route FusedBNAct through csrc/bn_act_v2.cu (ReLU bit mask) for one test."""
+    from eventgrad_b200.ops import bn_act
+    monkeypatch.setenv("EGB_BN_V2", "1")
+    bn_act._WS.clear()                      # the switch is read when the per-device workspace is created
+    yield
+    bn_act._WS.clear()
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (7, 128, 16, 16), (5, 256, 8, 8), (3, 512, 4, 4), (2, 2048, 4, 4),
+                                   (1, 64, 3, 5), (128, 64, 32, 32), (64, 128, 16, 16), (256, 64, 32, 32)])
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False), (False, True)])
+def test_bn_v2_forward_backward(shape, relu, res, bn_v2):
+    """Same acceptance test as the default kernels (tests/test_gpu_bn.py) on the v2 code path."""
+    from test_gpu_bn import test_fused_bn_act_forward_backward as body
+    from eventgrad_b200.ops import bn_act
+    body(shape, relu, res)
+    assert bn_act._WS[torch.device("cuda", torch.cuda.current_device())]["v2"] is True
+
+
+def test_bn_v2_matches_v1_bitwise_forward(bn_v2):
+    """v2's forward is the same arithmetic as the split v1 path: y must be bit-identical; dx within bf16."""
+    from eventgrad_b200.ops import bn_act
+    from eventgrad_b200.ops.bn_act import FusedBNAct
+    from test_gpu_bn import _mk
+    x, r, dy = _mk(128, 128, 16, 16, seed=5)
+    outs = []
+    for v2 in (True, False):
+        os.environ["EGB_BN_V2"] = "1" if v2 else "0"
+        bn_act._WS.clear()
+        bn = FusedBNAct(128).cuda().train()
+        xa, ra = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+        y = bn(xa, residual=ra, relu=True)
+        y.backward(dy)
+        outs.append((y.detach().clone(), xa.grad.clone(), ra.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()))
+    a, b = outs
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[2], b[2])                                   # dres = masked dy: exact in both
+    torch.testing.assert_close(a[4], b[4], rtol=1e-5, atol=1e-5)     # dbeta: same sums, different split
+    torch.testing.assert_close(a[3], b[3], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(a[1].float(), b[1].float(), rtol=2e-2, atol=2e-3)
+
+
+def test_bn_v2_resnet_step_and_graph(bn_v2):
+    """Flagship step (bf16 NHWC, whole-step CUDA graph, grad table) on the v2 BN kernels: loss finite and
+    parameters close to the v1 run from the same seed."""
+    from eventgrad_b200.ops import bn_act
+    from eventgrad_b200.config import preset
+    from eventgrad_b200.data import synthetic_source
+    from eventgrad_b200.engine.trainer import Trainer
+    from eventgrad_b200.utils.dist import DistEnv
+    res = {}
+    for v2 in (True, False):
+        os.environ["EGB_BN_V2"] = "1" if v2 else "0"
+        bn_act._WS.clear()
+        cfg = preset("cifar_event", backend="p2p", device="cuda", train_samples=512, test_samples=128, batch_size=64,
+                     epochs=100, quiet=True, max_steps=6, augment=False, dtype="bf16", channels_last=True,
+                     cuda_graph=True)
+        torch.manual_seed(0)
+        tr = Trainer(cfg, DistEnv(0, 1, 0, torch.device("cuda", 0), "none"),
+                     train_source=synthetic_source("cifar10", 512).pin(),
+                     test_source=synthetic_source("cifar10", 128, train=False).pin())
+        tr.fit()
+        tr.backend.check_status()
+        res[v2] = (float(tr.last_loss), tr.arena.theta.clone())
+        tr.close()
+    assert all(l == l and abs(l) < 1e4 for l, _ in res.values())
+    assert abs(res[True][0] - res[False][0]) < 0.2 * max(1.0, abs(res[False][0]))
+    rel = float((res[True][1] - res[False][1]).norm() / res[False][1].norm())
+    assert rel < 2e-3, rel
