@@ -79,6 +79,20 @@ def main():
         del arena, be
         torch.cuda.empty_cache()
 
+    # ---- experimental: double-buffered dense gossip (no WAR ack), opt-in --------------------------
+    if os.environ.get("EGB_EXPERIMENTAL") == "1":
+        cfg = TrainConfig(algo="decent", sync_mode="iter", double_buffer=True, **base).validate()
+        arena, be = make(cfg, env, a.model)
+        assert be.dbuf
+        n_bytes = arena.table.n_elems * 4
+        ms = timed(be.step, env, a.iters)
+        be.check_status()
+        res["gossip_dense_dbuf"] = {"ms": ms, "egress_GBps_per_gpu": 2 * n_bytes / ms / 1e6,
+                                    "frac_of_770": 2 * n_bytes / ms / 1e6 / 770, "grid": be.grid}
+        be.close()
+        del arena, be
+        torch.cuda.empty_cache()
+
     # ---- push-only kernel (phase 1): the ceiling of SM-issued NVLink stores, vs grid size ----------
     cfg = TrainConfig(algo="decent", sync_mode="iter", overlap_push=True, **base).validate()
     arena, be = make(cfg, env, a.model)

@@ -52,6 +52,8 @@ class TrainConfig:
                                      # shadow weights under dtype=bf16) instead of an fp32 grad arena
     overlap_push: bool = False       # p2p: launch the push half of the step on a side stream so it
                                      # overlaps forward/backward (False = single fused kernel)
+    double_buffer: bool = False      # EXPERIMENTAL (decent, p2p, iter-sync, fused step): two inbox slots,
+                                     # no WAR ack (csrc/gossip_dbuf.cu); not yet run on hardware
     # ---- data --------------------------------------------------------------
     data: str = "synthetic"          # synthetic | path to dataset root
     sampler: str = "random"          # random | sequential
@@ -146,6 +148,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--backend", default=None, choices=["auto", "p2p", "nccl", "gloo", "refport"])
     p.add_argument("--sync-mode", default=None, choices=["iter", "async"])
     p.add_argument("--overlap-push", action="store_true", default=None)
+    p.add_argument("--double-buffer", action="store_true", default=None)
     p.add_argument("--no-grad-table", dest="grad_table", action="store_false", default=None)
     p.add_argument("--data", default=None, help="'synthetic' or dataset root directory")
     p.add_argument("--sampler", default=None, choices=["random", "sequential"])

@@ -96,6 +96,10 @@ struct GossipParams {
 
 int gossip_max_grid(int device);  // co-resident CTAs (persistent grid upper bound)
 cudaError_t launch_gossip_step(const GossipParams& p, int grid, cudaStream_t s);
+// experimental double-buffered dense variant (csrc/gossip_dbuf.cu): inbox_l/inbox_r/push_l/push_r address
+// TWO consecutive slots of n_tiles*EG_TILE floats; requires phase 0, sync, do_push, do_mix, fsm disabled
+int gossip_dbuf_max_grid(int device);
+cudaError_t launch_gossip_step_dbuf(const GossipParams& p, int grid, cudaStream_t s);
 // (re)compute tile_ss (+ shadow) from theta and evaluate the trigger for step pass_num+1.
 cudaError_t launch_gossip_init(const GossipParams& p, int grid, int run_fsm, cudaStream_t s);
 // Trigger FSM alone with externally supplied norms (unit tests against the oracle).

@@ -141,6 +141,10 @@ PYBIND11_MODULE(_C, m) {
     p.phase = phase;
     check(launch_gossip_step(p, grid, S(s)), "gossip_step_phase");
   });
+  m.def("gossip_dbuf_max_grid", &gossip_dbuf_max_grid);
+  m.def("gossip_step_dbuf", [](const GossipParams& p, int grid, uintptr_t s) {
+    check(launch_gossip_step_dbuf(p, grid, S(s)), "gossip_step_dbuf");
+  });
   m.def("gossip_init", [](const GossipParams& p, int grid, int run_fsm, uintptr_t s) {
     check(launch_gossip_init(p, grid, run_fsm, S(s)), "gossip_init");
   });

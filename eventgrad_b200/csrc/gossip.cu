@@ -16,8 +16,22 @@
 //   4. norm-on-write: per-warp sum theta_new^2 partials; the last CTA reduces them per tensor
 //               in fixed order and runs the trigger FSM for the NEXT step (event.cpp:300-355),
 //               so the step needs no extra pass over theta, no grid sync and no host sync.
+//
+// This file is compiled twice.  As gossip.cu it is the default kernel described above.  csrc/gossip_dbuf.cu
+// defines EG_DBUF and includes it again to build the EXPERIMENTAL double-buffered dense variant
+// (`gossip_step_kernel_dbuf`, decent only): the inbox has two slots, slot = step & 1, and the WAR ack
+// (PROTOCOL.md 1.3) disappears -- a sender can be at most one step ahead of a receiver's reads because
+// finishing step k+1 needs the receiver's flags of step k+1 (model-checked: tests/test_protocol_model.py).
 #include "api.h"
 #include "common.cuh"
+
+#ifdef EG_DBUF
+#define EG_SYM(name) name##_dbuf
+#define EG_SLOT_OFF(p, step) ((size_t)((step) & 1) * ((size_t)(p).tab.n_tiles * EG_TILE))
+#else
+#define EG_SYM(name) name
+#define EG_SLOT_OFF(p, step) ((size_t)0)
+#endif
 
 namespace egb {
 
@@ -168,6 +182,11 @@ __device__ __forceinline__ void push_tile(const GossipParams& p, size_t base, co
     st_f8_v4(p.push_r + base, th);
   }
 }
+#ifdef EG_DBUF
+__device__ __forceinline__ void push_tile_slot(const GossipParams& p, size_t base, const F8& th, int step) {
+  push_tile(p, EG_SLOT_OFF(p, step) + base, th);
+}
+#endif
 
 __device__ __forceinline__ TileInfo resolve_tile(const GossipParams& p, int t) {
   TileInfo ti;
@@ -242,8 +261,13 @@ __device__ __forceinline__ void mix_tile(const GossipParams& p, int t, const Til
   // issue every load of the tile before the first dependent FP op (5 x 32 B in flight per lane)
   F8 L, R, m;
   if (p.do_mix) {
+#ifdef EG_DBUF
+    L = ld_f8_cg(p.inbox_l + EG_SLOT_OFF(p, step) + base);
+    R = ld_f8_cg(p.inbox_r + EG_SLOT_OFF(p, step) + base);
+#else
     L = ld_f8_cg(p.inbox_l + base);
     R = ld_f8_cg(p.inbox_r + base);
+#endif
   }
   const F8 g = load_grad(p, ti, base, threadIdx.x);
   if (kMom) m = ld_f8(p.mom + base);
@@ -312,12 +336,14 @@ __device__ __forceinline__ void grid_tail(const GossipParams& p, int step) {
   if (threadIdx.x == 0) {
     *p.ticket = 0u;
     *p.fsm.pass_num = step;
+#ifndef EG_DBUF
     if (p.sync && p.send_ack) {
       // every CTA of this rank has finished reading its inboxes for `step`
       fence_sys();
       st_release_sys(p.ack_to_l, (uint32_t)step);
       st_release_sys(p.ack_to_r, (uint32_t)step);
     }
+#endif
   }
 }
 
@@ -358,17 +384,21 @@ __device__ __forceinline__ void push_phase(const GossipParams& p, int step) {
 }
 
 template <bool kMom>
-__global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const GossipParams p) {
+__global__ void __launch_bounds__(EG_THREADS, 4) EG_SYM(gossip_step_kernel)(const GossipParams p) {
   const int b = blockIdx.x, G = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int step = *p.fsm.pass_num + 1;
   const int n_tiles = p.tab.n_tiles;
   const bool push = p.do_push != 0 && p.phase != 2;
 
+#ifdef EG_DBUF
+  if (p.phase != 0 || !(p.sync && push)) return;   // the launcher rejects these; never reached
+#else
   if (p.phase == 1) {
     push_phase(p, step);
     return;
   }
+#endif
   __shared__ TileInfo s_ti[EG_TI_CACHE];
   fill_tile_cache(p, s_ti);
   if (p.phase == 2 && p.sync && p.do_push) {
@@ -397,6 +427,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
     // neighbours' flags of that slice (normally long set -- the ring is symmetric) and mixes it.
     // Warps never wait for each other, so flag latency and the sys-scope fence of one warp hide
     // behind the streaming of the other 31 warps on the SM.
+#ifndef EG_DBUF
     __shared__ int s_ok;
     if (tid == 0) {
       // WAR guard: neighbours must have consumed what I pushed at step-1 before I overwrite it
@@ -405,6 +436,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
       s_ok = ok;
     }
     __syncthreads();
+#endif
     const int D = p.group_iters;                   // pipeline depth in tiles
     const int iters = (n_tiles + G - 1) / G;
     for (int j = 0; j < iters + D; ++j) {
@@ -413,7 +445,11 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
         const bool fired = (tile_info(p, s_ti, j, t).flags & 1) != 0;
         if (fired) {
           const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+#ifdef EG_DBUF
+          push_tile_slot(p, base, ld_f8(p.theta + base), step);
+#else
           push_tile(p, base, ld_f8(p.theta + base));
+#endif
         }
         __syncwarp();
         if (lane == 0) {
@@ -438,6 +474,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) gossip_step_kernel(const Gossip
   grid_tail(p, step);
 }
 
+#ifndef EG_DBUF
 // (Re)compute tile partials (+ bf16 shadow) from theta; optionally evaluate the trigger for the
 // first step.  Used once at start-up and after theta is modified outside the step kernel
 // (checkpoint restore).
@@ -503,5 +540,27 @@ cudaError_t launch_fsm_decide(const FsmDev& f, const TableDev& t, const float* e
   fsm_decide_kernel<<<1, EG_THREADS, 0, s>>>(f, t, ext_norm);
   return cudaGetLastError();
 }
+
+#else   // EG_DBUF: only the step kernel + its launcher exist in this translation unit
+int gossip_dbuf_max_grid(int device) {
+  int sms = 0, a = 0, b = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gossip_step_kernel_dbuf<true>, EG_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, gossip_step_kernel_dbuf<false>, EG_THREADS, 0);
+  if (b < a) a = b;
+  if (a < 1) a = 1;
+  return sms * a;
+}
+
+// Dense iter-sync exchange only (decent): every tensor fires every step, inboxes hold 2 slots.
+cudaError_t launch_gossip_step_dbuf(const GossipParams& p, int grid, cudaStream_t s) {
+  if (p.phase != 0 || !p.sync || !p.do_push || !p.do_mix || p.fsm.enabled) return cudaErrorInvalidValue;
+  if (p.mu != 0.f && p.mom != nullptr)
+    gossip_step_kernel_dbuf<true><<<grid, EG_THREADS, 0, s>>>(p);
+  else
+    gossip_step_kernel_dbuf<false><<<grid, EG_THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+#endif
 
 }  // namespace egb

@@ -28,14 +28,21 @@ def _table_of(model) -> TensorTable:
     return TensorTable.from_named(list(model.named_parameters()), TILE)
 
 
+def _wants_dbuf(cfg) -> bool:
+    """csrc/gossip_dbuf.cu applies to the dense, iter-sync, single-kernel decent step only."""
+    return (bool(getattr(cfg, "double_buffer", False)) and cfg.algo == "decent" and cfg.sync_mode == "iter"
+            and not getattr(cfg, "overlap_push", False))
+
+
 def build_layout(table: TensorTable, cfg, world: int, max_grid: int) -> Layout:
     lay = Layout()
     n = table.n_padded * 4
     lay.add("theta", n)
     lay.add("grad", n)
     if cfg.algo in ("decent", "event"):
-        lay.add("inbox_l", n)
-        lay.add("inbox_r", n)
+        slots = 2 if _wants_dbuf(cfg) else 1      # experimental double-buffered decent: slot = step & 1
+        lay.add("inbox_l", n * slots)
+        lay.add("inbox_r", n * slots)
     if cfg.algo == "spevent":
         K = sum(table.topk_counts(cfg.topk_percent))
         lay.add("rec_from_l", 2 * K * 4)
@@ -62,6 +69,8 @@ def preallocate_arena_buffers(model, cfg, env, group=None, bootstrap=None):
     C = ext()
     table = _table_of(model)
     max_grid = C.gossip_max_grid(env.device.index or 0)
+    if _wants_dbuf(cfg):
+        max_grid = min(max_grid, C.gossip_dbuf_max_grid(env.device.index or 0))
     lay = build_layout(table, cfg, env.world, max_grid)
     win = Window(lay, env.rank, env.world, env.device)
     theta = win.view("theta", torch.float32)
@@ -102,6 +111,7 @@ class P2PBackend(CommBackend):
         # split step: everything that depends only on theta_k (pushes / top-k records) is launched on a
         # side stream at the start of the step and overlaps forward+backward
         self.overlap = bool(getattr(cfg, "overlap_push", False)) and self.do_comm
+        self.dbuf = _wants_dbuf(cfg) and self.do_comm
         self.push_grid = push_grid
         self.recv_rms = cfg.dataset == "mnist"
         dev = self.dev
@@ -359,6 +369,8 @@ class P2PBackend(CommBackend):
                 C.gossip_step(self.gp, self.grid, s)
             elif self.overlap:
                 C.gossip_step_phase(self.gp, 2, self.grid, s)
+            elif self.dbuf:
+                C.gossip_step_dbuf(self.gp, self.grid, s)
             else:
                 C.gossip_step(self.gp, self.grid, s)
 

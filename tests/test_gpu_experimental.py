@@ -127,3 +127,28 @@ def test_bn_v2_resnet_step_and_graph(bn_v2):
     assert abs(res[True][0] - res[False][0]) < 0.2 * max(1.0, abs(res[False][0]))
     rel = float((res[True][1] - res[False][1]).norm() / res[False][1].norm())
     assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4])
+@pytest.mark.parametrize("mu", [0.0, 0.9])
+@pytest.mark.parametrize("model", ["cnn2", "mlp"])
+def test_double_buffered_decent_bitwise_vs_simulator(R, mu, model):
+    """csrc/gossip_dbuf.cu (two inbox slots, no WAR ack) on R virtual ranks of one GPU: same bits as the
+    oracle after 7 steps (odd and even slots both used several times)."""
+    from test_gpu_kernels import _cfg, _grads, _mask_pad, _world
+    from eventgrad_b200.engine.simulator import RingSimulator
+    cfg = _cfg("decent", momentum=mu, model=model, double_buffer=True)
+    w = _world(cfg, R, model=model)
+    assert all(be.dbuf for be in w.backends)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "decent", lr=cfg.lr, momentum=mu, serial_skip=False)
+    for s in range(7):
+        g = _mask_pad(w, _grads(R, t.n_padded, 300 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g])
+    torch.cuda.synchronize()
+    for be in w.backends:
+        be.check_status()
+    for r in range(R):
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r} theta differs"
+    w.close()
