@@ -14,8 +14,19 @@
 //
 // Cross-rank barriers are per CTA index (CTA b of every rank handles the same tile set), built
 // from monotonically increasing release/acquire flags in peer-mapped memory.
+//
+// Compiled twice: as allreduce.cu (above), and from csrc/allreduce_nvls.cu with EG_NVLS defined, which
+// builds the EXPERIMENTAL NVLink-SHARP variant `allreduce_nvls_kernel`: the tile owner reduces with ONE
+// `multimem.ld_reduce` on the multicast address (the NVSwitch adds the R copies) and broadcasts the average
+// with ONE `multimem.st` -- 2N/R bytes per GPU through the switch instead of 2(R-1)N/R over peer loads.
 #include "api.h"
 #include "common.cuh"
+
+#ifdef EG_NVLS
+#define EG_AR_SYM(name) name##_nvls
+#else
+#define EG_AR_SYM(name) name
+#endif
 
 namespace egb {
 
@@ -65,8 +76,35 @@ __device__ __forceinline__ F8 reduce_tile(const AllReduceParams& p, size_t base)
   return acc;
 }
 
+#ifdef EG_NVLS
+// sum over all ranks' copies of the 8 floats at multicast address `mc` (in-switch reduction), / world
+__device__ __forceinline__ F8 nvls_reduce_tile(const float* mc, float world) {
+  F8 a;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3])
+               : "l"(mc)
+               : "memory");
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(a.v[4]), "=f"(a.v[5]), "=f"(a.v[6]), "=f"(a.v[7])
+               : "l"(mc + 4)
+               : "memory");
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a.v[e] = __fdiv_rn(a.v[e], world);
+  return a;
+}
+// one store, delivered to every rank's copy by the switch
+__device__ __forceinline__ void nvls_broadcast_tile(float* mc, const F8& a) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(a.v[0]), "f"(a.v[1]),
+               "f"(a.v[2]), "f"(a.v[3])
+               : "memory");
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + 4), "f"(a.v[4]), "f"(a.v[5]),
+               "f"(a.v[6]), "f"(a.v[7])
+               : "memory");
+}
+#endif
+
 template <bool kMom>
-__global__ void __launch_bounds__(EG_THREADS, 4) allreduce_kernel(const AllReduceParams p) {
+__global__ void __launch_bounds__(EG_THREADS, 4) EG_AR_SYM(allreduce_kernel)(const AllReduceParams p) {
   const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
   const uint32_t seq = (uint32_t)(*p.step_ctr) + 1u;
   F8 zero;
@@ -92,8 +130,12 @@ __global__ void __launch_bounds__(EG_THREADS, 4) allreduce_kernel(const AllReduc
     for (int t = b; t < p.n_tiles; t += G, ++j) {
       if ((b + j) % p.world != p.rank) continue;          // tile owner
       const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+#ifdef EG_NVLS
+      nvls_broadcast_tile(p.mc_local + base, nvls_reduce_tile(p.mc_local + base, (float)p.world));
+#else
       const F8 g = reduce_tile(p, base);
       for (int r = 0; r < p.world; ++r) st_f8(p.peer_bufs[r] + base, g);   // broadcast the average
+#endif
     }
     cta_barrier_all_ranks(p, 1, b, G, seq);               // all owners of my tile set have stored
     if (p.mode == 1) {
@@ -117,6 +159,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) allreduce_kernel(const AllReduc
   }
 }
 
+#ifndef EG_NVLS
 cudaError_t launch_allreduce(const AllReduceParams& p, int grid, cudaStream_t s) {
   if (p.mode == 1 && p.mu != 0.f && p.mom != nullptr)
     allreduce_kernel<true><<<grid, EG_THREADS, 0, s>>>(p);
@@ -124,5 +167,16 @@ cudaError_t launch_allreduce(const AllReduceParams& p, int grid, cudaStream_t s)
     allreduce_kernel<false><<<grid, EG_THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
+#else
+// two-shot only; p.mc_local = multicast mapping of `local` (torch symmetric memory, see parallel/window.py)
+cudaError_t launch_allreduce_nvls(const AllReduceParams& p, int grid, cudaStream_t s) {
+  if (!p.two_shot || p.mc_local == nullptr) return cudaErrorInvalidValue;
+  if (p.mode == 1 && p.mu != 0.f && p.mom != nullptr)
+    allreduce_kernel_nvls<true><<<grid, EG_THREADS, 0, s>>>(p);
+  else
+    allreduce_kernel_nvls<false><<<grid, EG_THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+#endif
 
 }  // namespace egb

@@ -127,8 +127,11 @@ struct AllReduceParams {
   int mode;                 // 0: average in place   1: average + SGD (+ zero grad)
   int two_shot;             // 0: every rank reads all peers   1: reduce-scatter + broadcast
   int zero_after;
+  float* mc_local;          // NVLS variant only: multicast (NVSwitch) mapping of `local`; null otherwise
 };
 cudaError_t launch_allreduce(const AllReduceParams& p, int grid, cudaStream_t s);
+// experimental NVLink-SHARP variant (csrc/allreduce_nvls.cu): multimem.ld_reduce + multimem.st, two-shot only
+cudaError_t launch_allreduce_nvls(const AllReduceParams& p, int grid, cudaStream_t s);
 
 // ------------------------------------------------------------------ sparse (top-k) exchange
 struct SparseParams {

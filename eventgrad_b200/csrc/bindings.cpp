@@ -65,7 +65,7 @@ static const std::unordered_map<std::string, Setter<AllReduceParams>> kAllReduce
     PTRF(AllReduceParams, step_ctr), NUMF(AllReduceParams, timeout_ns), NUMF(AllReduceParams, n_tiles),
     NUMF(AllReduceParams, rank), NUMF(AllReduceParams, world), NUMF(AllReduceParams, lr),
     NUMF(AllReduceParams, mu), NUMF(AllReduceParams, mode), NUMF(AllReduceParams, two_shot),
-    NUMF(AllReduceParams, zero_after),
+    NUMF(AllReduceParams, zero_after), PTRF(AllReduceParams, mc_local),
 };
 
 static const std::unordered_map<std::string, Setter<SparseParams>> kSparse = {
@@ -153,6 +153,9 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("allreduce", [](const AllReduceParams& p, int grid, uintptr_t s) {
     check(launch_allreduce(p, grid, S(s)), "allreduce");
+  });
+  m.def("allreduce_nvls", [](const AllReduceParams& p, int grid, uintptr_t s) {
+    check(launch_allreduce_nvls(p, grid, S(s)), "allreduce_nvls");
   });
   m.def("sparse_select_push", [](const SparseParams& p, int grid, uintptr_t s) {
     check(launch_sparse_select_push(p, grid, S(s)), "sparse_select_push");

@@ -18,7 +18,7 @@ import torch
 
 from .arena import TILE, ParamArena, TensorTable
 from .base import CommBackend, StepLog
-from .window import DistBootstrap, Layout, Window
+from .window import DistBootstrap, Layout, SymmWindow, Window, wants_symm_window
 
 ONE_SHOT_MAX_BYTES = 512 * 1024        # above this the all-reduce switches to two-shot
 DEFAULT_TIMEOUT_NS = 30_000_000_000    # a wedged peer trips the sticky status instead of hanging
@@ -72,7 +72,8 @@ def preallocate_arena_buffers(model, cfg, env, group=None, bootstrap=None):
     if _wants_dbuf(cfg):
         max_grid = min(max_grid, C.gossip_dbuf_max_grid(env.device.index or 0))
     lay = build_layout(table, cfg, env.world, max_grid)
-    win = Window(lay, env.rank, env.world, env.device)
+    symm = wants_symm_window(env) and bootstrap is None      # EXPERIMENTAL NVLS path (EGB_NVLS=1)
+    win = (SymmWindow if symm else Window)(lay, env.rank, env.world, env.device)
     theta = win.view("theta", torch.float32)
     grad = win.view("grad", torch.float32)
     return theta, grad, {"window": win, "max_grid": max_grid, "bootstrap": bootstrap}
@@ -112,6 +113,7 @@ class P2PBackend(CommBackend):
         # side stream at the start of the step and overlaps forward+backward
         self.overlap = bool(getattr(cfg, "overlap_push", False)) and self.do_comm
         self.dbuf = _wants_dbuf(cfg) and self.do_comm
+        self.nvls = self.nvls_step = False      # set in connect() when the window has a multicast mapping
         self.push_grid = push_grid
         self.recv_rms = cfg.dataset == "mnist"
         dev = self.dev
@@ -284,6 +286,15 @@ class P2PBackend(CommBackend):
         av.update({"peer_bufs": P(self.d_peer_theta), "local": P(a.theta), "mode": 0, "zero_after": 0,
                    "two_shot": 1})
         self.ap_avg = av
+        # EXPERIMENTAL NVLS: multicast mappings of the same buffers (0 unless the window is a SymmWindow on
+        # a fabric with multicast support) -> csrc/allreduce_nvls.cu for the two-shot launches
+        mc_grad = win.mc_addr("grad") if hasattr(win, "mc_addr") else 0
+        mc_theta = win.mc_addr("theta") if hasattr(win, "mc_addr") else 0
+        self.nvls = bool(mc_grad) and W > 1
+        if self.nvls:
+            ap.update({"mc_local": mc_grad})
+            av.update({"mc_local": mc_theta})
+        self.nvls_step = self.nvls and t.n_padded * 4 > ONE_SHOT_MAX_BYTES
         self._connected = True
         if self.gossip or self.table_mode:
             self._init_norms(run_fsm=self.gossip)
@@ -358,7 +369,7 @@ class P2PBackend(CommBackend):
         with torch.cuda.device(self.dev):
             if self.cfg.algo == "cent":
                 if self.ring.world > 1:
-                    C.allreduce(self.ap, self.grid, s)
+                    (C.allreduce_nvls if self.nvls_step else C.allreduce)(self.ap, self.grid, s)
                 else:
                     C.gossip_step(self.gp, self.grid, s)       # plain fused SGD
                 return
@@ -398,7 +409,7 @@ class P2PBackend(CommBackend):
         if self.ring.world == 1:
             return
         with torch.cuda.device(self.dev):
-            self.C.allreduce(self.ap_avg, self.grid, self._stream())
+            (self.C.allreduce_nvls if self.nvls else self.C.allreduce)(self.ap_avg, self.grid, self._stream())
         if not self.cfg.final_divide_all and self.ring.rank != 0:
             self.arena.theta.mul_(float(self.ring.world))     # reference quirk Q5: only rank 0 divides
         if self.table_mode and getattr(self.arena, "shadow", None) is not None:

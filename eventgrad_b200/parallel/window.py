@@ -114,6 +114,68 @@ class Window:
             pass
 
 
+class SymmWindow(Window):
+    """EXPERIMENTAL (EGB_NVLS=1): the slab lives in torch symmetric memory instead of cudaMalloc + CUDA IPC.
+    The rendezvous maps every peer's slab (same role as the IPC handles) AND, on NVSwitch systems, a
+    MULTICAST address of the slab: a `multimem.ld_reduce` on it is reduced inside the switch and a
+    `multimem.st` is delivered to all ranks -- the NVLS path of csrc/allreduce_nvls.cu.  Everything else
+    (layout, views, peer addresses) is identical to `Window`, so all other kernels run unchanged."""
+
+    def __init__(self, layout: Layout, rank: int, world: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        from ..ops import ext
+        self._C = ext()
+        self.layout, self.rank, self.world, self.device = layout, rank, world, device
+        nbytes = max(256, layout.size)
+        self._t = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self._t.zero_()                                   # window starts zeroed, like ipc_alloc
+        torch.cuda.synchronize(device)
+        self.raw = self._t
+        self.ptr = self._t.data_ptr()
+        self.handle = None
+        self.peer_ptrs: List[int] = [0] * world
+        self.peer_ptrs[rank] = self.ptr
+        self.mc_ptr = 0
+        self._hdl = None
+        self._opened: List[int] = []
+        self._closed = False
+
+    def rendezvous(self, group=None) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass                                          # newer torch enables groups implicitly
+        hdl = symm.rendezvous(self._t, group)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.ptr:
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected peer table")
+        self.peer_ptrs = ptrs
+        self.mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        self._hdl = hdl
+
+    def mc_addr(self, name: str) -> int:
+        """Multicast address of a section (0 when the fabric has no multicast support)."""
+        return 0 if not self.mc_ptr else self.mc_ptr + self.layout.offset(name)
+
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            torch.cuda.synchronize(self.device)
+        except Exception:
+            pass
+        self.raw = self._t = self._hdl = None
+
+
+def wants_symm_window(env) -> bool:
+    import os
+    return os.environ.get("EGB_NVLS", "0") == "1" and env.world > 1 and getattr(env, "backend", "") != "local"
+
+
 class DistBootstrap:
     def __init__(self, env, group=None):
         self.rank, self.world, self.group = env.rank, env.world, group
@@ -127,8 +189,11 @@ class DistBootstrap:
         return out
 
     def connect(self, win: Window) -> None:
-        handles = self.all_gather_object(win.handle)
-        win.connect_handles(handles)
+        if isinstance(win, SymmWindow):
+            win.rendezvous(self.group)
+        else:
+            handles = self.all_gather_object(win.handle)
+            win.connect_handles(handles)
         if self.world > 1:
             import torch.distributed as dist
             dist.barrier(group=self.group)

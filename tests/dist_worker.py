@@ -36,13 +36,15 @@ def main():
     ap.add_argument("--warm", type=int, default=4)
     ap.add_argument("--sync-mode", default="iter")
     ap.add_argument("--overlap", action="store_true")
+    ap.add_argument("--double-buffer", action="store_true")
     a = ap.parse_args()
     dev_pref = "cpu" if (a.backend == "gloo" or os.environ.get("EGB_WORKER_CPU") == "1") else "cuda"
     env = init_distributed(dev_pref)
     cfg = TrainConfig(algo=a.algo, dataset=a.dataset, model=a.model, lr=0.05, momentum=a.momentum,
                       horizon=a.horizon, thres_type=a.thres_type, constant=a.constant,
                       topk_percent=a.topk, initial_comm_passes=a.warm, backend=a.backend,
-                      sync_mode=a.sync_mode, overlap_push=a.overlap).validate()
+                      sync_mode=a.sync_mode, overlap_push=a.overlap,
+                      double_buffer=a.double_buffer).validate()
     torch.manual_seed(0)
     model = build_model(a.model)
     ring = Ring(env.rank, env.world)
@@ -123,7 +125,9 @@ def main():
                     ok = False
                     print(f"BYTES rank {r}: {int(allev[r][1])} vs {sim.bytes[r]}")
         print("WORKER_OK" if ok else "WORKER_FAIL", f"algo={a.algo} backend={a.backend} world={W} "
-              f"events={sum(int(e[0]) for e in allev)} dense={sim.dense_messages()}", flush=True)
+              f"events={sum(int(e[0]) for e in allev)} dense={sim.dense_messages()} "
+              f"nvls={int(getattr(be, 'nvls', False))} nvls_step={int(getattr(be, 'nvls_step', False))} "
+              f"dbuf={int(getattr(be, 'dbuf', False))}", flush=True)
     # final averaging must agree across ranks
     if a.algo != "cent":
         be.final_average()

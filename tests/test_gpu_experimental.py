@@ -152,3 +152,46 @@ def test_double_buffered_decent_bitwise_vs_simulator(R, mu, model):
     for r in range(R):
         assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r} theta differs"
     w.close()
+
+
+def _torchrun(world, *args, env=None, timeout=600):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29891",
+           os.path.join(root, "tests", "dist_worker.py"), *args]
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=root, env=e)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "WORKER_OK" in out, out[-3000:]
+    return out
+
+
+@pytest.mark.multigpu
+def test_double_buffered_decent_multi_gpu():
+    """csrc/gossip_dbuf.cu over real NVLink peers: bit-exact vs the simulator."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    for w in [x for x in (2, 4, 8) if x <= n]:
+        out = _torchrun(w, "--algo", "decent", "--backend", "p2p", "--steps", "11", "--double-buffer")
+        assert "dbuf=1" in out
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("algo", ["cent", "decent"])
+def test_nvls_allreduce_multi_gpu(algo):
+    """EGB_NVLS=1: window in torch symmetric memory, csrc/allreduce_nvls.cu (multimem.ld_reduce/st) for the
+    cent step on the ResNet arena (two-shot) and for the final parameter averaging."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    w = max(x for x in (2, 4, 8) if x <= n)
+    out = _torchrun(w, "--algo", algo, "--backend", "p2p", "--model", "resnet18", "--dataset", "cifar10", "--steps", "3",
+                    env={"EGB_NVLS": "1"})
+    if "nvls=1" not in out:
+        pytest.skip("no multicast support on this fabric (window fell back to plain peer mappings)")
+    if algo == "cent":
+        assert "nvls_step=1" in out
