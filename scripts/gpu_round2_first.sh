@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-2 kick-off on ONE GPU (gpurun --timeout 2400 -- 'bash scripts/gpu_round2_first.sh'), ~15-20 GPU-min.
+# 1. default GPU suite (must stay green)  2. every EXPERIMENTAL kernel written blind at the end of round 1
+# (each group under its own timeout so a hang cannot eat the call)  3. A/B benches for the ones that pass.
+# Everything lands in gpurun_out/round2_first/.
+O=gpurun_out/round2_first; mkdir -p $O
+python -m eventgrad_b200.build_ext > $O/build.txt 2>&1
+timeout 1200 python -m pytest tests -m "gpu and not multigpu" -x -q --timeout 600 > $O/pytest_default.txt 2>&1; echo "default suite rc=$?"; tail -3 $O/pytest_default.txt
+for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet double_buffered_decent_bitwise linear_tc_tma native_loader p2p_file_write; do
+  EGB_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_gpu_experimental.py -q --timeout 300 -k "$k" > $O/exp_$k.txt 2>&1
+  echo "experimental $k rc=$? : $(tail -1 $O/exp_$k.txt)"
+done
+bench() { name=$1; shift; timeout 600 env "$@" python bench.py --gpus 1 --steps 30 --warmup 5 > $O/bench_$name.txt 2>&1
+  tail -1 $O/bench_$name.txt | python -c "
+import sys,json
+try:
+    d=json.loads(sys.stdin.read()); print('$name', 'img/s', round(d['value']), 'ms', round(d['ms_per_step'],3), 'e2e', d.get('e2e',{}).get('value'), 'clk', d.get('clocks'))
+except Exception as e: print('$name FAILED', e)
+"; }
+bench default EGB_BN_V2=0
+bench bn_v2 EGB_BN_V2=1
+bench default_again EGB_BN_V2=0
+timeout 300 python benchmarks/linear_tc_bench.py > $O/linear_default.txt 2>&1; tail -5 $O/linear_default.txt
+EGB_TC_LINEAR=tma timeout 300 python benchmarks/linear_tc_bench.py > $O/linear_tma.txt 2>&1; tail -5 $O/linear_tma.txt

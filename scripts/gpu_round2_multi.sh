@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-2, N GPUs (gpurun --gpus 8 --timeout 1500 -- 'bash scripts/gpu_round2_multi.sh 8'): re-measure the
+# headline at N with the final code, then the experimental multi-GPU paths (double-buffered decent, NVLS).
+N=${1:-8}; O=gpurun_out/round2_multi$N; mkdir -p $O
+run() { name=$1; shift; timeout 600 env $ENVV python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 298$((30+RANDOM%60)) bench.py --gpus $N --steps 40 --warmup 5 "$@" > $O/bench_$name.txt 2>&1; tail -1 $O/bench_$name.txt | python -c "
+import sys,json
+try:
+    d=json.loads(sys.stdin.read()); print('$name', 'value', round(d['value']), 'ms', round(d['ms_per_step'],3), 'e2e', d.get('e2e',{}).get('value'), 'clk', d.get('clocks'))
+except Exception as e: print('$name FAILED', e)
+"; }
+ENVV="EGB_BN_V2=0" run dpsgd_overlap --overlap on
+ENVV="EGB_BN_V2=0" run dpsgd_fused --overlap off --no-e2e
+ENVV="EGB_BN_V2=0" run nccl --impl nccl --no-e2e
+ENVV="EGB_BN_V2=0" run refport --impl refport --no-e2e
+ENVV="EGB_BN_V2=0" run cent --algo cent --no-e2e
+EGB_TEST_WORLDS=$N EGB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -q --timeout 500 -k "multi_gpu" > $O/exp_multi.txt 2>&1; echo "experimental multi rc=$?"; tail -4 $O/exp_multi.txt
+EGB_EXPERIMENTAL=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29821 benchmarks/exchange_bw.py --iters 40 --out $O/exchange_bw.json > $O/exchange.txt 2>&1; tail -60 $O/exchange.txt | grep -v "^\*\|OMP_NUM\|^$"
+ENVV="EGB_NVLS=1" run cent_nvls --algo cent --no-e2e
