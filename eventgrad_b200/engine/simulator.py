@@ -19,7 +19,7 @@ from ..parallel.trigger import (TriggerConfig, TriggerState, mix3_, sgd_, topk_s
 class RingSimulator:
     def __init__(self, world: int, theta0: torch.Tensor, table: TensorTable, algo: str,
                  tcfg: Optional[TriggerConfig] = None, lr: float = 1e-2, momentum: float = 0.0,
-                 topk_percent: float = 10.0, serial_skip: bool = True):
+                 topk_percent: float = 10.0, serial_skip: bool = True, sparse_init=None):
         assert algo in ("cent", "decent", "event", "spevent")
         self.R, self.table, self.algo = world, table, algo
         self.tcfg = tcfg or TriggerConfig()
@@ -34,9 +34,12 @@ class RingSimulator:
         self.fire_history: List[List[torch.Tensor]] = []
         if algo == "spevent":
             self.k = table.topk_counts(topk_percent)
-            self.prev = [theta0.clone() for _ in range(world)]
-            self.rep_l = [theta0.clone() for _ in range(world)]
-            self.rep_r = [theta0.clone() for _ in range(world)]
+            # default: everything starts from theta_0; sparse_init=(prev, left, right) mirrors the reference's
+            # three extra randomly initialised networks (quirk Q8, identical on every rank: same seed)
+            p0, l0, r0 = sparse_init if sparse_init is not None else (theta0, theta0, theta0)
+            self.prev = [p0.clone() for _ in range(world)]
+            self.rep_l = [l0.clone() for _ in range(world)]
+            self.rep_r = [r0.clone() for _ in range(world)]
         elif algo in ("decent", "event"):
             self.inbox_l = [torch.zeros_like(theta0) for _ in range(world)]
             self.inbox_r = [torch.zeros_like(theta0) for _ in range(world)]

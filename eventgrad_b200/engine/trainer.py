@@ -55,6 +55,11 @@ class Trainer:
         # identical initial weights on every rank: torch::manual_seed(0) (event.cpp:115)
         torch.manual_seed(cfg.seed)
         self.model = build_model(cfg.model, resnet_variant=cfg.resnet_variant)
+        extra = None
+        if cfg.algo == "spevent" and cfg.spevent_fresh_replicas:
+            # quirk Q8: prev_model, left_model, right_model are constructed right after the model, in this
+            # order, from the same RNG stream (spevent.cpp:123-136)
+            extra = [build_model(cfg.model, resnet_variant=cfg.resnet_variant) for _ in range(3)]
         want_p2p = cfg.backend == "p2p" or (cfg.backend == "auto" and dev.type == "cuda")
         theta_buf = grad_buf = None
         self._symm = None
@@ -69,6 +74,9 @@ class Trainer:
             pass  # activations are produced NHWC by the loader; conv weights already NHWC views
         self.backend = make_backend(cfg, self.arena, self.ring, env, group) if not want_p2p else \
             self._make_p2p(group)
+        if extra is not None:
+            self.backend.set_sparse_init(*[self.arena.pack(m) for m in extra])
+            del extra
         # ---- data ------------------------------------------------------------------
         self.train_src = train_source or load_source(cfg.dataset, cfg.data, cfg.train_samples, True)
         self.test_src = test_source

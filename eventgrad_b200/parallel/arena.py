@@ -155,6 +155,17 @@ class ParamArena:
             return flat.view(o, h, w, c).permute(0, 3, 1, 2)
         return flat.view(shp)
 
+    def pack(self, other: nn.Module) -> torch.Tensor:
+        """Flat copy (arena layout, padding lanes zero) of ANOTHER model with the same architecture."""
+        out = torch.zeros_like(self.theta)
+        named = list(other.named_parameters())
+        if [tuple(p.shape) for _, p in named] != [tuple(s) for s in self.table.shapes]:
+            raise ValueError("pack(): model does not match the arena's tensor table")
+        with torch.no_grad():
+            for i, (_, p) in enumerate(named):
+                self.view(out, i).copy_(p.detach().to(out.device))
+        return out
+
     def flat(self, buf: torch.Tensor, i: int) -> torch.Tensor:
         t = self.table
         return buf[t.offsets[i]: t.offsets[i] + t.numels[i]]

@@ -57,6 +57,18 @@ class CommBackend:
     def bytes_sent(self) -> int:
         return 0
 
+    def set_sparse_init(self, prev, rep_l, rep_r) -> None:
+        """spevent only, reference quirk Q8 (spevent.cpp:123-136): start the 'previously sent' copy and the two
+        neighbour replicas from the given flat tensors (three more random networks in the reference)
+        instead of theta_0.  Must be called before the first step."""
+        if self.cfg.algo != "spevent" or not hasattr(self, "prev"):
+            raise RuntimeError("set_sparse_init applies to the spevent algorithm only")
+        if self.pass_num != 0:
+            raise RuntimeError("set_sparse_init must be called before the first step")
+        self.prev.copy_(prev.to(self.prev.device))
+        self.rep_l.copy_(rep_l.to(self.rep_l.device))
+        self.rep_r.copy_(rep_r.to(self.rep_r.device))
+
     def drain_logs(self) -> List[StepLog]:
         out, self.logs = self.logs, []
         return out

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--sync-mode", default="iter")
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--double-buffer", action="store_true")
+    ap.add_argument("--fresh-replicas", action="store_true")
     a = ap.parse_args()
     dev_pref = "cpu" if (a.backend == "gloo" or os.environ.get("EGB_WORKER_CPU") == "1") else "cuda"
     env = init_distributed(dev_pref)
@@ -47,6 +48,7 @@ def main():
                       double_buffer=a.double_buffer).validate()
     torch.manual_seed(0)
     model = build_model(a.model)
+    extra = [build_model(a.model) for _ in range(3)] if a.fresh_replicas else None
     ring = Ring(env.rank, env.world)
     if a.backend == "p2p":
         from eventgrad_b200.parallel.p2p import P2PBackend, preallocate_arena_buffers
@@ -58,6 +60,11 @@ def main():
         be = make_backend(cfg, arena, ring, env)
     t = arena.table
     theta0 = arena.theta.detach().cpu().clone()
+    sparse_init = None
+    if extra is not None:
+        packed = [arena.pack(m) for m in extra]
+        be.set_sparse_init(*packed)
+        sparse_init = tuple(x.detach().cpu().clone() for x in packed)
     mask = torch.zeros(t.n_padded)
     for o, n in zip(t.offsets, t.numels):
         mask[o:o + n] = 1
@@ -100,7 +107,7 @@ def main():
     ok = True
     if env.rank == 0:
         sim = RingSimulator(W, theta0, t, a.algo, TriggerConfig.from_train(cfg), lr=cfg.lr, momentum=cfg.momentum,
-                            topk_percent=a.topk, serial_skip=(a.dataset == "cifar10"))
+                            topk_percent=a.topk, serial_skip=(a.dataset == "cifar10"), sparse_init=sparse_init)
         for s in range(a.steps):
             fo = [allf[r][s].bool().cpu() for r in range(W)] if allf is not None else None
             sim.step([grad_of(s, r) for r in range(W)], fires=fo)

@@ -26,6 +26,13 @@ def test_collective_backend_matches_simulator(algo, world):
     assert rc == 0 and "WORKER_OK" in out, out[-2000:]
 
 
+def test_spevent_fresh_replicas_quirk_matches_simulator():
+    """Reference quirk Q8 (spevent.cpp:123-136): prev/left/right start as three MORE random networks."""
+    rc, out = _torchrun(3, [os.path.join(ROOT, "tests", "dist_worker.py")], "--algo", "spevent",
+                        "--backend", "gloo", "--steps", "8", "--fresh-replicas")
+    assert rc == 0 and "WORKER_OK" in out, out[-2000:]
+
+
 def test_cent_program_end_to_end_world2(tmp_path):
     """BASELINE config 1: dmnist/cent AllReduce MLP on CPU/gloo world_size=2."""
     rc, out = _torchrun(2, ["-m", "eventgrad_b200.cli.cent"], "--epochs", "6", "--train-samples", "2000",
