@@ -83,8 +83,12 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int N = p.N;
   const uint32_t a_bytes = TM_ROWS * TM_BK * 2, b_bytes = (uint32_t)N * TM_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;              // multiples of 1024 (N % 16 == 0 -> b_bytes % 2048 == 0)
-  const uint32_t smem0 = s_u32(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TM_STAGES * stage_bytes);
+  // SWIZZLE_128B atoms (TMA destination and UMMA descriptors, base_offset = 0) need 1024-byte aligned tiles;
+  // the dynamic-smem base is only guaranteed 16-byte aligned, so round up (the launcher adds 1 KB of slack)
+  const uint32_t smem_unaligned = s_u32(smem_raw);
+  const uint32_t smem0 = (smem_unaligned + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_raw + (smem0 - smem_unaligned);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TM_STAGES * stage_bytes);
   const uint32_t full0 = s_u32(bars), empty0 = full0 + 8u * TM_STAGES;
   const uint32_t tfull0 = empty0 + 8u * TM_STAGES, tempty0 = tfull0 + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TM_STAGES + 4);
