@@ -195,3 +195,61 @@ def test_nvls_allreduce_multi_gpu(algo):
         pytest.skip("no multicast support on this fabric (window fell back to plain peer mappings)")
     if algo == "cent":
         assert "nvls_step=1" in out
+
+
+def test_conv_split_backward_matches_default(monkeypatch):
+    """ops/shadow.py:_ConvSplitBwd (wgrad on a side stream, dgrad on the main stream) vs the default autograd
+    path of the same ShadowConv2d: same cuDNN kernels -> gradients equal to bf16 precision, run 20 times to give
+    a stream-ordering bug a chance to show."""
+    from eventgrad_b200.ops.shadow import ShadowConv2d
+    torch.manual_seed(1)
+    conv = ShadowConv2d(64, 128, 3, stride=2, padding=1, bias=False).cuda()
+    conv.w16 = conv.weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    x0 = torch.randn(32, 64, 16, 16, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = None
+    res = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("EGB_CONV_SPLIT_BWD", split)
+        outs = []
+        for _ in range(20 if split == "1" else 1):
+            x = x0.clone().requires_grad_(True)
+            conv.w16.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = conv(x)
+            if dy is None:
+                dy = torch.randn_like(y)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            outs.append((y.detach().float(), x.grad.float().clone(), conv.w16.grad.float().clone()))
+        res[split] = outs
+    ref = res["0"][0]
+    for y, dx, dw in res["1"]:
+        torch.testing.assert_close(y, ref[0], rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(dx, ref[1], rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(dw, ref[2], rtol=2e-2, atol=5e-2)
+
+
+def test_conv_split_backward_resnet_graph_step(monkeypatch):
+    """Whole flagship step (per-GPU batch 32, CUDA graph, grad table) with the split backward: parameters after
+    6 steps track the default run from the same seed."""
+    from eventgrad_b200.config import preset
+    from eventgrad_b200.data import synthetic_source
+    from eventgrad_b200.engine.trainer import Trainer
+    from eventgrad_b200.utils.dist import DistEnv
+    res = {}
+    for split in ("1", "0"):
+        monkeypatch.setenv("EGB_CONV_SPLIT_BWD", split)
+        cfg = preset("cifar_event", backend="p2p", device="cuda", train_samples=256, test_samples=64, batch_size=32,
+                     epochs=100, quiet=True, max_steps=6, augment=False, dtype="bf16", channels_last=True,
+                     cuda_graph=True)
+        torch.manual_seed(0)
+        tr = Trainer(cfg, DistEnv(0, 1, 0, torch.device("cuda", 0), "none"),
+                     train_source=synthetic_source("cifar10", 256).pin(),
+                     test_source=synthetic_source("cifar10", 64, train=False).pin())
+        tr.fit()
+        tr.backend.check_status()
+        res[split] = (float(tr.last_loss), tr.arena.theta.clone())
+        tr.close()
+    assert all(l == l and abs(l) < 1e4 for l, _ in res.values())
+    rel = float((res["1"][1] - res["0"][1]).norm() / res["0"][1].norm())
+    assert rel < 2e-3, rel
