@@ -48,6 +48,9 @@ def parse():
                    help="split step: pushes on a side stream overlapping forward/backward "
                         "(auto = on for N >= 2: measured 2.65 vs 2.83 ms/step at N=2, 1.95 vs 2.22 at N=4, "
                         "1.89 vs 2.09 at N=8)")
+    p.add_argument("--ce-push", action="store_true",
+                   help="experimental: copy-engine push in the split step (decent + overlap)")
+    p.add_argument("--double-buffer", action="store_true", help="experimental: ack-free double-buffered decent step")
     p.add_argument("--no-channels-last", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--out", default="")
@@ -96,6 +99,7 @@ def main():
                  horizon=args.horizon, topk_percent=args.topk,
                  overlap_push=(args.overlap == "on") or (args.overlap == "auto" and N >= 2 and backend == "p2p"),
                  channels_last=not args.no_channels_last, cuda_graph=not args.no_graph,
+                 ce_push=args.ce_push, double_buffer=args.double_buffer,
                  train_samples=n_train, test_samples=256, quiet=True, augment=True)
     src = synthetic_source("cifar10", n_train).pin()
     tr = Trainer(cfg, env, train_source=src)

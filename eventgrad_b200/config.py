@@ -54,6 +54,8 @@ class TrainConfig:
                                      # overlaps forward/backward (False = single fused kernel)
     spevent_fresh_replicas: bool = False   # reference quirk Q8: prev/left/right replicas of spevent are three
                                      # MORE randomly initialised networks (spevent.cpp:123-136) instead of theta_0
+    ce_push: bool = False            # EXPERIMENTAL (decent + overlap_push): the push half of the split step is two
+                                     # copy-engine memcpys instead of an SM kernel (csrc/ce_push.cu)
     double_buffer: bool = False      # EXPERIMENTAL (decent, p2p, iter-sync, fused step): two inbox slots,
                                      # no WAR ack (csrc/gossip_dbuf.cu); not yet run on hardware
     # ---- data --------------------------------------------------------------
@@ -151,6 +153,7 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--sync-mode", default=None, choices=["iter", "async"])
     p.add_argument("--overlap-push", action="store_true", default=None)
     p.add_argument("--double-buffer", action="store_true", default=None)
+    p.add_argument("--ce-push", action="store_true", default=None)
     p.add_argument("--fresh-replicas", dest="spevent_fresh_replicas", action="store_true", default=None,
                    help="spevent: initialise prev/left/right replicas like the reference (three more random nets)")
     p.add_argument("--no-grad-table", dest="grad_table", action="store_false", default=None)

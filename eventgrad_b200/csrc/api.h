@@ -98,6 +98,8 @@ int gossip_max_grid(int device);  // co-resident CTAs (persistent grid upper bou
 cudaError_t launch_gossip_step(const GossipParams& p, int grid, cudaStream_t s);
 // experimental double-buffered dense variant (csrc/gossip_dbuf.cu): inbox_l/inbox_r/push_l/push_r address
 // TWO consecutive slots of n_tiles*EG_TILE floats; requires phase 0, sync, do_push, do_mix, fsm disabled
+// experimental copy-engine push of the split step (csrc/ce_push.cu): ack wait -> 2 x cudaMemcpyAsync -> flags
+cudaError_t launch_ce_push(const GossipParams& p, cudaStream_t s);
 int gossip_dbuf_max_grid(int device);
 cudaError_t launch_gossip_step_dbuf(const GossipParams& p, int grid, cudaStream_t s);
 // (re)compute tile_ss (+ shadow) from theta and evaluate the trigger for step pass_num+1.

@@ -141,6 +141,7 @@ PYBIND11_MODULE(_C, m) {
     p.phase = phase;
     check(launch_gossip_step(p, grid, S(s)), "gossip_step_phase");
   });
+  m.def("ce_push", [](const GossipParams& p, uintptr_t s) { check(launch_ce_push(p, S(s)), "ce_push"); });
   m.def("gossip_dbuf_max_grid", &gossip_dbuf_max_grid);
   m.def("gossip_step_dbuf", [](const GossipParams& p, int grid, uintptr_t s) {
     check(launch_gossip_step_dbuf(p, grid, S(s)), "gossip_step_dbuf");

@@ -113,6 +113,7 @@ class P2PBackend(CommBackend):
         # side stream at the start of the step and overlaps forward+backward
         self.overlap = bool(getattr(cfg, "overlap_push", False)) and self.do_comm
         self.dbuf = _wants_dbuf(cfg) and self.do_comm
+        self.ce_push = bool(getattr(cfg, "ce_push", False)) and self.overlap and cfg.algo == "decent" and self.sync
         self.nvls = self.nvls_step = False      # set in connect() when the window has a multicast mapping
         self.push_grid = push_grid
         self.recv_rms = cfg.dataset == "mnist"
@@ -358,6 +359,8 @@ class P2PBackend(CommBackend):
         with torch.cuda.device(self.dev):
             if self.sparse:
                 C.sparse_select_push(self.sp, self.grid, s)
+            elif self.ce_push:
+                C.ce_push(self.gp, s)                       # experimental: DMA engines instead of an SM kernel
             else:
                 g = self.push_grid or max(1, min(self.grid, 128))
                 C.gossip_step_phase(self.gp, 1, g, s)

@@ -6,7 +6,7 @@
 O=gpurun_out/round2_first; mkdir -p $O
 python -m eventgrad_b200.build_ext > $O/build.txt 2>&1
 timeout 1200 python -m pytest tests -m "gpu and not multigpu" -x -q --timeout 600 > $O/pytest_default.txt 2>&1; echo "default suite rc=$?"; tail -3 $O/pytest_default.txt
-for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet double_buffered_decent_bitwise conv_split linear_tc_tma native_loader p2p_file_write; do
+for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet double_buffered_decent_bitwise ce_push_split conv_split linear_tc_tma native_loader p2p_file_write; do
   EGB_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_gpu_experimental.py -q --timeout 300 -k "$k" > $O/exp_$k.txt 2>&1
   echo "experimental $k rc=$? : $(tail -1 $O/exp_$k.txt)"
 done

@@ -10,6 +10,8 @@ except Exception as e: print('$name FAILED', e)
 "; }
 ENVV="EGB_BN_V2=0" run dpsgd_overlap --overlap on
 ENVV="EGB_BN_V2=0" run dpsgd_fused --overlap off --no-e2e
+ENVV="EGB_BN_V2=0" run dpsgd_overlap_ce --overlap on --ce-push --no-e2e
+ENVV="EGB_BN_V2=0" run dpsgd_fused_dbuf --overlap off --double-buffer --no-e2e
 ENVV="EGB_BN_V2=0" run nccl --impl nccl --no-e2e
 ENVV="EGB_BN_V2=0" run refport --impl refport --no-e2e
 ENVV="EGB_BN_V2=0" run cent --algo cent --no-e2e

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--double-buffer", action="store_true")
     ap.add_argument("--fresh-replicas", action="store_true")
+    ap.add_argument("--ce-push", action="store_true")
     a = ap.parse_args()
     dev_pref = "cpu" if (a.backend == "gloo" or os.environ.get("EGB_WORKER_CPU") == "1") else "cuda"
     env = init_distributed(dev_pref)
@@ -45,7 +46,7 @@ def main():
                       horizon=a.horizon, thres_type=a.thres_type, constant=a.constant,
                       topk_percent=a.topk, initial_comm_passes=a.warm, backend=a.backend,
                       sync_mode=a.sync_mode, overlap_push=a.overlap,
-                      double_buffer=a.double_buffer).validate()
+                      double_buffer=a.double_buffer, ce_push=a.ce_push).validate()
     torch.manual_seed(0)
     model = build_model(a.model)
     extra = [build_model(a.model) for _ in range(3)] if a.fresh_replicas else None
@@ -134,7 +135,7 @@ def main():
         print("WORKER_OK" if ok else "WORKER_FAIL", f"algo={a.algo} backend={a.backend} world={W} "
               f"events={sum(int(e[0]) for e in allev)} dense={sim.dense_messages()} "
               f"nvls={int(getattr(be, 'nvls', False))} nvls_step={int(getattr(be, 'nvls_step', False))} "
-              f"dbuf={int(getattr(be, 'dbuf', False))}", flush=True)
+              f"dbuf={int(getattr(be, 'dbuf', False))} ce_push={int(getattr(be, 'ce_push', False))}", flush=True)
     # final averaging must agree across ranks
     if a.algo != "cent":
         be.final_average()
