@@ -11,7 +11,7 @@ for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet double_buffered_decen
   echo "experimental $k rc=$? : $(tail -1 $O/exp_$k.txt)"
 done
 bench() { name=$1; shift; timeout 600 env "$@" python bench.py --gpus 1 --steps 30 --warmup 5 $BARGS > $O/bench_$name.txt 2>&1
-  tail -1 $O/bench_$name.txt | python -c "
+  grep '^{"metric"' $O/bench_$name.txt | tail -1 | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); print('$name', 'img/s', round(d['value']), 'ms', round(d['ms_per_step'],3), 'e2e', d.get('e2e',{}).get('value'), 'clk', d.get('clocks'))

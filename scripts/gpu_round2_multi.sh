@@ -2,7 +2,7 @@
 # Round-2, N GPUs (gpurun --gpus 8 --timeout 1500 -- 'bash scripts/gpu_round2_multi.sh 8'): re-measure the
 # headline at N with the final code, then the experimental multi-GPU paths (double-buffered decent, NVLS).
 N=${1:-8}; O=gpurun_out/round2_multi$N; mkdir -p $O
-run() { name=$1; shift; timeout 600 env $ENVV python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 298$((30+RANDOM%60)) bench.py --gpus $N --steps 40 --warmup 5 "$@" > $O/bench_$name.txt 2>&1; tail -1 $O/bench_$name.txt | python -c "
+run() { name=$1; shift; timeout 600 env $ENVV python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 298$((30+RANDOM%60)) bench.py --gpus $N --steps 40 --warmup 5 "$@" > $O/bench_$name.txt 2>&1; grep '^{"metric"' $O/bench_$name.txt | tail -1 | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); print('$name', 'value', round(d['value']), 'ms', round(d['ms_per_step'],3), 'e2e', d.get('e2e',{}).get('value'), 'clk', d.get('clocks'))
