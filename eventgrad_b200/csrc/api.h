@@ -228,6 +228,9 @@ struct BnParamsV2 {
 };
 // which: 0 training forward, 2 backward
 cudaError_t launch_bn_v2(const BnParamsV2& p, int which, int sm_count, cudaStream_t s);
+// single-launch thread-block-cluster / DSMEM variant (experimental, csrc/bn_act_cluster.cu); *taken = 0 when the
+// slice does not fit one cluster's shared memory -- the caller then uses launch_bn_v2
+cudaError_t launch_bn_cluster(const BnParamsV2& p, int which, cudaStream_t s, int* taken);
 
 // ------------------------------------------------------------------ tcgen05 fused Linear(+bias)(+ReLU)
 // Y[M,N] = act(X[M,K] * W[N,K]^T + b): bf16 operands, fp32 accumulation in TMEM (csrc/linear_tc.cu).

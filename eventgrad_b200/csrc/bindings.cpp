@@ -223,7 +223,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("bn_forward_v2", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, uintptr_t gamma, uintptr_t beta,
                             uintptr_t mean, uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt,
                             uintptr_t partial, uintptr_t ticket, uintptr_t status, long long M, int C, float eps,
-                            float momentum, int relu, int sm_count, uintptr_t s) {
+                            float momentum, int relu, int sm_count, int cluster, uintptr_t s) {
     BnParamsV2 pp;
     std::memset(&pp, 0, sizeof(pp));
     BnParams& p = pp.b;
@@ -242,12 +242,15 @@ PYBIND11_MODULE(_C, m) {
     p.ticket = reinterpret_cast<unsigned int*>(ticket);
     p.status = reinterpret_cast<int*>(status);
     p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu;
-    check(launch_bn_v2(pp, 0, sm_count, S(s)), "bn_forward_v2");
+    int taken = 0;
+    if (cluster) check(launch_bn_cluster(pp, 0, S(s), &taken), "bn_forward_cluster");
+    if (!taken) check(launch_bn_v2(pp, 0, sm_count, S(s)), "bn_forward_v2");
+    return taken;
   });
   m.def("bn_backward_v2", [](uintptr_t x, uintptr_t mask, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
                              uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
                              uintptr_t ticket, uintptr_t status, long long M, int C, int relu, int sm_count,
-                             uintptr_t s) {
+                             int cluster, uintptr_t s) {
     BnParamsV2 pp;
     std::memset(&pp, 0, sizeof(pp));
     BnParams& p = pp.b;
@@ -265,7 +268,10 @@ PYBIND11_MODULE(_C, m) {
     p.ticket = reinterpret_cast<unsigned int*>(ticket);
     p.status = reinterpret_cast<int*>(status);
     p.M = M; p.C = C; p.relu = relu;
-    check(launch_bn_v2(pp, 2, sm_count, S(s)), "bn_backward_v2");
+    int taken = 0;
+    if (cluster) check(launch_bn_cluster(pp, 2, S(s), &taken), "bn_backward_cluster");
+    if (!taken) check(launch_bn_v2(pp, 2, sm_count, S(s)), "bn_backward_v2");
+    return taken;
   });
   m.def("linear_tc", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int M, int N, int K, int relu,
                         int out_bf16, uintptr_t s) {

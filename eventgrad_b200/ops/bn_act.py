@@ -38,7 +38,10 @@ def _workspace(device):
               "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0,
               # EXPERIMENTAL csrc/bn_act_v2.cu (ReLU bit mask instead of re-reading y in the backward);
               # opt-in until it has been validated on hardware (tests/test_gpu_experimental.py)
-              "v2": os.environ.get("EGB_BN_V2", "0") == "1"}
+              "v2": os.environ.get("EGB_BN_V2", "0") == "1",
+              # EXPERIMENTAL csrc/bn_act_cluster.cu on top of v2: one launch per direction (thread-block
+              # cluster + DSMEM) for tensors whose 64-channel slice fits one cluster's shared memory
+              "cluster": 1 if os.environ.get("EGB_BN_CLUSTER", "0") == "1" else 0, "cluster_taken": 0}
         _WS[device] = ws
     return ws
 
@@ -82,11 +85,12 @@ class _FusedBNActFn(torch.autograd.Function):
         if ctx.v2:
             mask = torch.empty(M * C // 8 if relu else 0, dtype=torch.uint8, device=x.device)
             with torch.cuda.device(x.device):
-                C_ext.bn_forward_v2(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
-                                    mask.data_ptr() if relu else 0, weight.data_ptr(), bias.data_ptr(),
-                                    mean.data_ptr(), invstd.data_ptr(), rm, rv, nb, ws["partial"].data_ptr(),
-                                    ws["f"][0], ws["status"], M, C, float(eps), float(momentum),
-                                    1 if relu else 0, ws["sm"], stream)
+                ws["cluster_taken"] += C_ext.bn_forward_v2(
+                    x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
+                    mask.data_ptr() if relu else 0, weight.data_ptr(), bias.data_ptr(),
+                    mean.data_ptr(), invstd.data_ptr(), rm, rv, nb, ws["partial"].data_ptr(),
+                    ws["f"][0], ws["status"], M, C, float(eps), float(momentum),
+                    1 if relu else 0, ws["sm"], ws["cluster"], stream)
             ctx.save_for_backward(x, mask, weight, mean, invstd)
             ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
             return y
@@ -118,11 +122,12 @@ class _FusedBNActFn(torch.autograd.Function):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         if ctx.v2:                                    # `y` is the bit mask here
             with torch.cuda.device(x.device):
-                C_ext.bn_backward_v2(x.data_ptr(), y.data_ptr() if ctx.relu else 0, dy.data_ptr(), dx.data_ptr(),
-                                     dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
-                                     invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                     ws["partial"].data_ptr(), ws["b"][0], ws["status"], M, C,
-                                     1 if ctx.relu else 0, ws["sm"], stream)
+                ws["cluster_taken"] += C_ext.bn_backward_v2(
+                    x.data_ptr(), y.data_ptr() if ctx.relu else 0, dy.data_ptr(), dx.data_ptr(),
+                    dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
+                    invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                    ws["partial"].data_ptr(), ws["b"][0], ws["status"], M, C,
+                    1 if ctx.relu else 0, ws["sm"], ws["cluster"], stream)
             return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
         with torch.cuda.device(x.device):
             C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),

@@ -6,7 +6,7 @@
 O=gpurun_out/round2_first; mkdir -p $O
 python -m eventgrad_b200.build_ext > $O/build.txt 2>&1
 timeout 1200 python -m pytest tests -m "gpu and not multigpu" -x -q --timeout 600 > $O/pytest_default.txt 2>&1; echo "default suite rc=$?"; tail -3 $O/pytest_default.txt
-for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet double_buffered_decent_bitwise ce_push_split conv_split linear_tc_tma native_loader p2p_file_write; do
+for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet bn_cluster double_buffered_decent_bitwise ce_push_split conv_split linear_tc_tma native_loader p2p_file_write; do
   EGB_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_gpu_experimental.py -q --timeout 300 -k "$k" > $O/exp_$k.txt 2>&1
   echo "experimental $k rc=$? : $(tail -1 $O/exp_$k.txt)"
 done
@@ -19,12 +19,15 @@ except Exception as e: print('$name FAILED', e)
 "; }
 bench default EGB_BN_V2=0
 bench bn_v2 EGB_BN_V2=1
+bench bn_v2_cluster EGB_BN_V2=1 EGB_BN_CLUSTER=1
 bench default_again EGB_BN_V2=0
 # per-GPU batch 32 (the 8-GPU configuration on one GPU): kernel-count bound, where the split conv backward could pay
 BARGS="--global-batch 32 --no-e2e"
 bench b32_default EGB_CONV_SPLIT_BWD=0
 bench b32_split_bwd EGB_CONV_SPLIT_BWD=1
 bench b32_split_bwd_bn_v2 EGB_CONV_SPLIT_BWD=1 EGB_BN_V2=1
+bench b32_bn_cluster EGB_BN_V2=1 EGB_BN_CLUSTER=1
+bench b32_all EGB_CONV_SPLIT_BWD=1 EGB_BN_V2=1 EGB_BN_CLUSTER=1
 BARGS=""
 timeout 300 python benchmarks/linear_tc_bench.py > $O/linear_default.txt 2>&1; tail -5 $O/linear_default.txt
 EGB_TC_LINEAR=tma timeout 300 python benchmarks/linear_tc_bench.py > $O/linear_tma.txt 2>&1; tail -5 $O/linear_tma.txt

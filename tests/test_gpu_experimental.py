@@ -285,3 +285,61 @@ def test_ce_push_multi_gpu():
     for w in [x for x in (2, 4, 8) if x <= n]:
         out = _torchrun(w, "--algo", "decent", "--backend", "p2p", "--steps", "10", "--overlap", "--ce-push")
         assert "ce_push=1" in out
+
+
+@pytest.fixture
+def bn_cluster(monkeypatch):
+    """FusedBNAct through csrc/bn_act_cluster.cu (single launch, thread-block cluster + DSMEM) where the slice fits."""
+    from eventgrad_b200.ops import bn_act
+    monkeypatch.setenv("EGB_BN_V2", "1")
+    monkeypatch.setenv("EGB_BN_CLUSTER", "1")
+    bn_act._WS.clear()
+    yield
+    bn_act._WS.clear()
+
+
+# (N, C, H, W): M = N*H*W rows.  cluster sizes exercised: 1 (M<=256), 2, 4, 8, 16 (M=16384 fwd: 8; bwd: 16 or fallback)
+@pytest.mark.parametrize("shape", [(1, 64, 3, 5), (2, 2048, 4, 4), (3, 512, 4, 4), (32, 512, 4, 4), (32, 256, 8, 8),
+                                   (32, 128, 16, 16), (7, 128, 16, 16), (64, 128, 16, 16), (32, 64, 32, 32)])
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False), (False, True)])
+def test_bn_cluster_forward_backward(shape, relu, res, bn_cluster):
+    """Same acceptance test as the default kernels on the cluster path; the last shape (32768 rows) must fall back."""
+    from test_gpu_bn import test_fused_bn_act_forward_backward as body
+    from eventgrad_b200.ops import bn_act
+    body(shape, relu, res)
+    ws = bn_act._WS[torch.device("cuda", torch.cuda.current_device())]
+    M = shape[0] * shape[2] * shape[3]
+    if M <= 8192:
+        assert ws["cluster_taken"] >= 1, "cluster kernel was not used for a shape that fits"
+    if M > 16 * 1536:
+        assert ws["cluster_taken"] == 0
+
+
+def test_bn_cluster_resnet_step_b32(bn_cluster):
+    """Flagship step at the per-GPU batch of the 8-GPU configuration with cluster BN: tracks the default run."""
+    from eventgrad_b200.ops import bn_act
+    from eventgrad_b200.config import preset
+    from eventgrad_b200.data import synthetic_source
+    from eventgrad_b200.engine.trainer import Trainer
+    from eventgrad_b200.utils.dist import DistEnv
+    res = {}
+    for mode in ("cluster", "default"):
+        os.environ["EGB_BN_V2"] = "1" if mode == "cluster" else "0"
+        os.environ["EGB_BN_CLUSTER"] = "1" if mode == "cluster" else "0"
+        bn_act._WS.clear()
+        cfg = preset("cifar_event", backend="p2p", device="cuda", train_samples=256, test_samples=64, batch_size=32,
+                     epochs=100, quiet=True, max_steps=6, augment=False, dtype="bf16", channels_last=True,
+                     cuda_graph=True)
+        torch.manual_seed(0)
+        tr = Trainer(cfg, DistEnv(0, 1, 0, torch.device("cuda", 0), "none"),
+                     train_source=synthetic_source("cifar10", 256).pin(),
+                     test_source=synthetic_source("cifar10", 64, train=False).pin())
+        tr.fit()
+        tr.backend.check_status()
+        if mode == "cluster":
+            assert bn_act._WS[torch.device("cuda", 0)]["cluster_taken"] > 0
+        res[mode] = (float(tr.last_loss), tr.arena.theta.clone())
+        tr.close()
+    assert all(l == l and abs(l) < 1e4 for l, _ in res.values())
+    rel = float((res["cluster"][1] - res["default"][1]).norm() / res["default"][1].norm())
+    assert rel < 2e-3, rel
