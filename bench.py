@@ -233,6 +233,12 @@ def main():
                    "algorithm": args.algo, "backend": backend, "sync_mode": cfg.sync_mode, "overlap_push": cfg.overlap_push,
                    "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": cfg.cuda_graph,
                    "channels_last": cfg.channels_last,
+                   # opt-in experimental paths active in this run (all off = the validated default code)
+                   "experimental": {k: v for k, v in {
+                       "bn_v2": os.environ.get("EGB_BN_V2") == "1", "bn_cluster": os.environ.get("EGB_BN_CLUSTER") == "1",
+                       "conv_split_bwd": os.environ.get("EGB_CONV_SPLIT_BWD") == "1",
+                       "nvls": os.environ.get("EGB_NVLS") == "1", "ce_push": bool(cfg.ce_push),
+                       "double_buffer": bool(cfg.double_buffer)}.items() if v},
                    "l2_policy": "per-step working set (theta,grad,mom,2 inboxes = "
                                 f"{5 * table.n_padded * 4 / 1e6:.0f} MB + activations) exceeds the 126 MB L2; "
                                 "no explicit flush"},
