@@ -156,3 +156,85 @@ def test_ack_free_double_buffered_dense_gossip_design(R, G, n_tiles, n_warps, de
         status, viol = run_double_buffered(R, G, n_tiles, n_warps, steps=5, depth=depth, seed=seed)
         assert status == "ok", (status, seed)
         assert not viol, viol[:3]
+
+
+def run_split_step(R, n_ctas, n_tiles, steps, seed, use_ack=True, fire_p=0.6, max_ticks=400000):
+    """PROTOCOL.md section 2 (also the copy-engine variant csrc/ce_push.cu, which keeps the same flags):
+    phase 1 = [ack wait] -> push every fired tile -> publish pushed=k; phase 2 (after phase 1 of the same step in
+    stream order) = wait pushed_from_{l,r} >= k -> every CTA mixes its tiles -> last CTA acks k.  Phase 1 of
+    step k+1 starts after phase 2 of step k (side.wait_stream(cur))."""
+    rng = random.Random(seed)
+    inbox = [{s: [0] * n_tiles for s in "lr"} for _ in range(R)]
+    pushed = [{s: 0 for s in "lr"} for _ in range(R)]
+    ack = [{s: 0 for s in "lr"} for _ in range(R)]
+    done2 = [0] * R                                   # CTAs of rank r that finished phase 2 (cumulative)
+    p1_done = [0] * R                                 # last step whose phase 1 completed on rank r
+    fire = {(r, t, k): rng.random() < fire_p for r in range(R) for t in range(n_tiles) for k in range(1, steps + 1)}
+    violations = []
+
+    def phase1(r):
+        L, Rn = (r - 1) % R, (r + 1) % R
+        for k in range(1, steps + 1):
+            yield lambda k=k: done2[r] >= n_ctas * (k - 1)                     # stream order: after phase 2 of k-1
+            if use_ack:
+                yield lambda k=k: ack[r]["l"] >= k - 1 and ack[r]["r"] >= k - 1
+            for t in range(n_tiles):
+                if fire[(r, t, k)]:
+                    inbox[L]["r"][t] = k
+                    inbox[Rn]["l"][t] = k
+                    yield None
+            pushed[L]["r"] = k
+            pushed[Rn]["l"] = k
+            p1_done[r] = k
+            yield None
+
+    def phase2(r, b):
+        L, Rn = (r - 1) % R, (r + 1) % R
+        for k in range(1, steps + 1):
+            yield lambda k=k: p1_done[r] >= k and done2[r] >= n_ctas * (k - 1)    # stream order
+            yield lambda k=k: pushed[r]["l"] >= k and pushed[r]["r"] >= k
+            for t in range(b, n_tiles, n_ctas):
+                for side, nb in (("l", L), ("r", Rn)):
+                    got = inbox[r][side][t]
+                    want = max([s for s in range(1, k + 1) if fire[(nb, t, s)]] or [0])
+                    if got != want:
+                        violations.append((r, side, t, k, got, want))
+                yield None
+            done2[r] += 1
+            if done2[r] == n_ctas * k:                                          # last CTA of the grid acks
+                ack[L]["r"] = k
+                ack[Rn]["l"] = k
+            yield None
+
+    actors = [phase1(r) for r in range(R)] + [phase2(r, b) for r in range(R) for b in range(n_ctas)]
+    pending = [next(a) for a in actors]
+    alive = set(range(len(actors)))
+    ticks = 0
+    while alive and ticks < max_ticks:
+        ready = [i for i in alive if pending[i] is None or pending[i]()]
+        if not ready:
+            return "deadlock", violations
+        i = rng.choice(ready)
+        try:
+            pending[i] = next(actors[i])
+        except StopIteration:
+            alive.discard(i)
+        ticks += 1
+    return ("ok" if not alive else "timeout"), violations
+
+
+@pytest.mark.parametrize("R,n_ctas,n_tiles", [(1, 2, 4), (2, 2, 5), (3, 3, 7), (5, 2, 4)])
+def test_split_step_protocol(R, n_ctas, n_tiles):
+    for seed in range(40):
+        status, viol = run_split_step(R, n_ctas, n_tiles, steps=5, seed=seed)
+        assert status == "ok", (status, seed)
+        assert not viol, viol[:3]
+
+
+def test_split_step_mutant_without_ack_is_caught():
+    caught = 0
+    for seed in range(80):
+        status, viol = run_split_step(3, 2, 5, steps=5, seed=seed, use_ack=False)
+        assert status == "ok"
+        caught += bool(viol)
+    assert caught > 0
