@@ -231,6 +231,7 @@ cudaError_t launch_bn_v2(const BnParamsV2& p, int which, int sm_count, cudaStrea
 // single-launch thread-block-cluster / DSMEM variant (experimental, csrc/bn_act_cluster.cu); *taken = 0 when the
 // slice does not fit one cluster's shared memory -- the caller then uses launch_bn_v2
 cudaError_t launch_bn_cluster(const BnParamsV2& p, int which, cudaStream_t s, int* taken);
+void bn_cluster_plan(long long M, int which, int* cs, long long* rows_per_cta, size_t* smem_bytes);
 
 // ------------------------------------------------------------------ tcgen05 fused Linear(+bias)(+ReLU)
 // Y[M,N] = act(X[M,K] * W[N,K]^T + b): bf16 operands, fp32 accumulation in TMEM (csrc/linear_tc.cu).

@@ -247,6 +247,13 @@ PYBIND11_MODULE(_C, m) {
     if (!taken) check(launch_bn_v2(pp, 0, sm_count, S(s)), "bn_forward_v2");
     return taken;
   });
+  m.def("bn_cluster_plan", [](long long M, int which) {
+    int cs = 0;
+    long long rows = 0;
+    size_t smem = 0;
+    bn_cluster_plan(M, which, &cs, &rows, &smem);
+    return py::make_tuple(cs, rows, smem);
+  });
   m.def("bn_backward_v2", [](uintptr_t x, uintptr_t mask, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
                              uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
                              uintptr_t ticket, uintptr_t status, long long M, int C, int relu, int sm_count,

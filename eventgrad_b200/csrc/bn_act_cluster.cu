@@ -257,6 +257,21 @@ __global__ void __launch_bounds__(BN_THREADS, 1) bn_cluster_bwd_kernel(const BnP
   }
 }
 
+// Host-side plan shared by the launcher and the CPU test: cluster size and rows per CTA for M rows, or cs = 0 when the
+// slice does not fit.  The kernels recompute rows_per with the same formula from cluster.num_blocks().
+void bn_cluster_plan(long long M, int which, int* cs_out, long long* rows_per_out, size_t* smem_out) {
+  const int slabs = (which == 0) ? 1 : 2;
+  const long long cap = (which == 0) ? BNC_FWD_ROWS : BNC_BWD_ROWS;
+  auto rows_per = [&](int cs) { return ((M + cs - 1) / cs + BN_RPP - 1) / BN_RPP * BN_RPP; };
+  int cs = 1;
+  while (cs < 8 && (M + cs - 1) / cs > 256) cs *= 2;    // ~256 rows per CTA: spread a slice over up to 8 SMs
+  while (cs < 16 && rows_per(cs) > cap) cs *= 2;
+  if (rows_per(cs) > cap) cs = 0;
+  *cs_out = cs;
+  *rows_per_out = cs ? rows_per(cs) : 0;
+  *smem_out = cs ? (size_t)rows_per(cs) * 128 * slabs : 0;
+}
+
 // -------------------------------------------------------------------------------------------
 // which: 0 training forward, 2 backward.  *taken = 1 if the single-launch cluster kernel was launched,
 // 0 if the shape does not fit (caller falls back to launch_bn_v2).
@@ -268,13 +283,11 @@ cudaError_t launch_bn_cluster(const BnParamsV2& pp, int which, cudaStream_t s, i
   if (p.relu && pp.mask == nullptr) return cudaErrorInvalidValue;
   static bool attr_done = false;
   static int max16_fwd = -1, max16_bwd = -1;            // is a 16-CTA cluster with full shared memory schedulable?
-  const int slabs = (which == 0) ? 1 : 2;
-  const long long cap = (which == 0) ? BNC_FWD_ROWS : BNC_BWD_ROWS;
-  auto rows_per = [&](int cs) { return ((p.M + cs - 1) / cs + BN_RPP - 1) / BN_RPP * BN_RPP; };
-  int cs = 1;
-  while (cs < 8 && (p.M + cs - 1) / cs > 256) cs *= 2;  // ~256 rows per CTA: spread a slice over up to 8 SMs
-  while (cs < 16 && rows_per(cs) > cap) cs *= 2;
-  if (rows_per(cs) > cap) return cudaSuccess;           // does not fit: not taken
+  int cs = 0;
+  long long rows_per_cta = 0;
+  size_t smem_bytes = 0;
+  bn_cluster_plan(p.M, which, &cs, &rows_per_cta, &smem_bytes);
+  if (cs == 0) return cudaSuccess;                      // does not fit: not taken
   if (!attr_done) {
     const int maxdyn = BNC_FWD_ROWS * 128;              // == BNC_BWD_ROWS * 256
     cudaError_t e = cudaFuncSetAttribute(bn_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn);
@@ -289,7 +302,7 @@ cudaError_t launch_bn_cluster(const BnParamsV2& pp, int which, cudaStream_t s, i
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(slices * cs));
   cfg.blockDim = dim3(BN_THREADS);
-  cfg.dynamicSmemBytes = (size_t)rows_per(cs) * 128 * slabs;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

@@ -65,3 +65,22 @@ def test_set_sparse_init_guards():
     sp.pass_num = 1
     with pytest.raises(RuntimeError):
         sp.set_sparse_init(z, z, z)
+
+
+def test_bn_cluster_plan_covers_every_row_and_fits_shared_memory():
+    """Host-side plan of csrc/bn_act_cluster.cu (pure host code in the extension, runs without a GPU)."""
+    from eventgrad_b200.ops import ext
+    C = ext()
+    for which, slabs, cap in ((0, 1, 1536), (2, 2, 768)):
+        for M in list(range(1, 600, 7)) + [1024, 2048, 4095, 4096, 8192, 12288, 12289, 16384, 24576, 24577, 32768, 262144]:
+            cs, rows, smem = C.bn_cluster_plan(M, which)
+            if cs == 0:
+                assert M > 16 * cap - 16 * 31, (M, which)        # only genuinely too-large slices are refused
+                continue
+            assert cs in (1, 2, 4, 8, 16)
+            assert rows % 32 == 0 and rows <= cap
+            assert cs * rows >= M                                   # every row has an owner
+            assert (cs - 1) * rows < M + rows                       # no more than one (partially) idle tail CTA chain
+            assert smem == rows * 128 * slabs <= 196608
+    assert C.bn_cluster_plan(2048, 0)[0] == 8                       # batch-32 stage 3: one slice over 8 SMs
+    assert C.bn_cluster_plan(8192, 2)[0] == 16                      # batch-32 stage 2 backward needs the 16-CTA cluster
