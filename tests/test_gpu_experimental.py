@@ -154,12 +154,16 @@ def test_double_buffered_decent_bitwise_vs_simulator(R, mu, model):
     w.close()
 
 
+_PORT = [29880]
+
+
 def _torchrun(world, *args, env=None, timeout=600):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _PORT[0] += 1
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29891",
+           "--master-addr", "127.0.0.1", "--master-port", str(_PORT[0]),
            os.path.join(root, "tests", "dist_worker.py"), *args]
     e = dict(os.environ)
     e.update(env or {})
