@@ -103,6 +103,11 @@ def main():
             be.C.gossip_step_phase(be.gp, 2, be.grid, be._stream())
         ms_both = timed(both, env, a.iters)
         res[f"push_only_grid{g}"] = {"ms_push_plus_mix": ms_both}
+    if os.environ.get("EGB_EXPERIMENTAL") == "1":
+        def both_ce():                                   # copy engines instead of the SM push kernel
+            be.C.ce_push(be.gp, be._stream())
+            be.C.gossip_step_phase(be.gp, 2, be.grid, be._stream())
+        res["push_copy_engine"] = {"ms_push_plus_mix": timed(both_ce, env, a.iters)}
     ms_mix = None
     be.check_status()
     be.close(); del arena, be; torch.cuda.empty_cache()
