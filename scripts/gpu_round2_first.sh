@@ -6,8 +6,12 @@
 O=gpurun_out/round2_first; mkdir -p $O
 python -m eventgrad_b200.build_ext > $O/build.txt 2>&1
 timeout 1200 python -m pytest tests -m "gpu and not multigpu" -x -q --timeout 600 > $O/pytest_default.txt 2>&1; echo "default suite rc=$?"; tail -3 $O/pytest_default.txt
-for k in bn_v2_forward_backward bn_v2_matches bn_v2_resnet bn_cluster double_buffered_decent_bitwise ce_push_split conv_split linear_tc_tma native_loader p2p_file_write; do
-  EGB_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_gpu_experimental.py -q --timeout 300 -k "$k" > $O/exp_$k.txt 2>&1
+# group:timeout(s) -- kernels that wait on mbarriers / cluster barriers have no device-side timeout, so a deadlock
+# costs the whole group timeout: keep those short
+for kt in bn_v2_forward_backward:300 bn_v2_matches:120 bn_v2_resnet:240 bn_cluster_forward_backward:240 bn_cluster_resnet:240 \
+          double_buffered_decent_bitwise:240 ce_push_split:180 conv_split:240 linear_tc_tma:150 native_loader:120 p2p_file_write:180; do
+  k=${kt%%:*}; t=${kt##*:}
+  EGB_EXPERIMENTAL=1 timeout $t python -m pytest tests/test_gpu_experimental.py -q --timeout $t -k "$k" > $O/exp_$k.txt 2>&1
   echo "experimental $k rc=$? : $(tail -1 $O/exp_$k.txt)"
 done
 bench() { name=$1; shift; timeout 600 env "$@" python bench.py --gpus 1 --steps 30 --warmup 5 $BARGS > $O/bench_$name.txt 2>&1
