@@ -34,7 +34,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "refport"],
                    help="ours: fused p2p kernels | nccl: batched torch.distributed baseline | refport: reference-"
-                        "structured per-tensor port (host sync per tensor) | reference: the unmodified reference (unavailable)")
+                        "structured per-tensor port (host sync per tensor) | reference: the unmodified reference C++ programs (baseline/_ref, CPU + shm MPI shim)")
     p.add_argument("--algo", default="dpsgd", choices=["dpsgd", "event", "spevent", "cent"])
     p.add_argument("--model", default="resnet18")
     p.add_argument("--global-batch", type=int, default=256)
@@ -59,13 +59,11 @@ def parse():
 
 
 def reference_arm(args):
-    # The reference is five C++ main() programs (LibTorch + MPI + OpenCV C++), with no setup.py /
-    # pyproject: `pip install --no-index ... /root/reference` fails ("not installable"), and the
-    # image has no MPI (mpi.h / mpirun), no OpenCV C++ headers and no datasets. See DESIGN.md.
-    print(json.dumps({"impl": "reference",
-                      "unavailable": "reference is not pip-installable (no setup.py/pyproject; C++ mains "
-                                     "need MPI + OpenCV C++ + dataset files, none present offline)"}))
-    return 0
+    # The unmodified reference, built by baseline/build_ref.py into baseline/_ref (shm MPI + OpenCV stand-ins); none of
+    # this repo's package is imported on this path.  Details: baseline/ref_arm.py, baseline/README.md.
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline"))
+    import ref_arm
+    return ref_arm.run(args)
 
 
 def main():
