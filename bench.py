@@ -15,6 +15,10 @@ One JSON line on rank 0.  `value` is timed on the device (CUDA events) over K wh
 (forward, backward, fused exchange+average+SGD) with inputs already resident; `e2e` repeats the
 measurement through the public Trainer API with, every step, the H2D copy of that step's uint8
 batch from pinned host memory, GPU decode/augmentation, and a D2H read of the loss.
+The headline runs at the reference's precision (fp32, TF32 off) with the Trainer's DEFAULT execution
+switches (on a GPU: NHWC + fused BN kernels, whole-step CUDA graph, overlapped pushes for N >= 2) -- the
+same configuration `python -m eventgrad_b200.cli.cifar_event` uses; bf16 / tf32 rows ride along under
+`other_dtypes`.  `--impl reference` times the unmodified reference C++ program (baseline/).
 """
 from __future__ import annotations
 
@@ -39,7 +43,12 @@ def parse():
     p.add_argument("--model", default="resnet18")
     p.add_argument("--global-batch", type=int, default=256)
     p.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "tf32"])
+    p.add_argument("--dtype", default="fp32", choices=["bf16", "fp32", "tf32"],
+                   help="compute dtype of forward/backward. fp32 (default) = IEEE fp32 with TF32 OFF, the reference's "
+                        "precision (event.cpp:279); the exchange / optimizer kernels are fp32 in every mode")
+    p.add_argument("--also", default="bf16,tf32",
+                   help="extra dtypes measured after the headline (device-timed only) and reported under "
+                        "`other_dtypes` in the same JSON line; '' to skip")
     p.add_argument("--sync-mode", default="iter", choices=["iter", "async"])
     p.add_argument("--horizon", type=float, default=1.0)
     p.add_argument("--topk", type=float, default=10.0)
@@ -48,9 +57,9 @@ def parse():
                    help="split step: pushes on a side stream overlapping forward/backward "
                         "(auto = on for N >= 2: measured 2.65 vs 2.83 ms/step at N=2, 1.95 vs 2.22 at N=4, "
                         "1.89 vs 2.09 at N=8)")
-    p.add_argument("--ce-push", action="store_true",
-                   help="experimental: copy-engine push in the split step (decent + overlap)")
-    p.add_argument("--double-buffer", action="store_true", help="experimental: ack-free double-buffered decent step")
+    p.add_argument("--ce-push", action="store_true", help="copy-engine push in the split step (decent + overlap)")
+    p.add_argument("--double-buffer", action=argparse.BooleanOptionalAction, default=None,
+                   help="fused (non-split) decent step: two inbox slots, no WAR ack (default on where it applies)")
     p.add_argument("--no-channels-last", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--out", default="")
@@ -66,44 +75,32 @@ def reference_arm(args):
     return ref_arm.run(args)
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return reference_arm(args)
-
+def measure(args, env, dtype, want_e2e, src, sample_clocks):
+    """One Trainer at `dtype`: device-timed K steps (+ optionally the end-to-end loop).  Returns a dict."""
     import torch
     from eventgrad_b200.config import preset
-    from eventgrad_b200.data import synthetic_source
     from eventgrad_b200.engine.trainer import Trainer
-    from eventgrad_b200.utils.clocks import ClockSampler
-    from eventgrad_b200.utils.dist import barrier, init_distributed, max_over_ranks, shutdown, sum_over_ranks
-
-    if not torch.cuda.is_available():
-        print(json.dumps({"impl": args.impl, "error": "bench.py needs a CUDA device (run it through gpurun / on the B200 box)"}))
-        return 2
-    env = init_distributed("cuda")
+    from eventgrad_b200.utils.clocks import NvmlClockSampler
+    from eventgrad_b200.utils.dist import barrier, max_over_ranks, sum_over_ranks
     N = env.world
-    if N != args.gpus and env.rank == 0:
-        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={N}", file=sys.stderr)
     gb = args.global_batch if args.scaling == "strong" else args.global_batch * N
     per_rank = max(1, gb // N)
     algo = {"dpsgd": "decent", "event": "event", "spevent": "spevent", "cent": "cent"}[args.algo]
     backend = {"ours": "p2p", "nccl": "nccl", "refport": "refport"}[args.impl]
-    steps_needed = args.warmup + args.steps + 2
-    n_train = max(per_rank * N * 8, 4096)
+    tri = {"auto": None, "on": True, "off": False}
     cfg = preset("cifar_event", algo=algo, model=args.model, backend=backend, device="cuda",
-                 dtype=args.dtype, batch_size=gb, batch_mode="global", epochs=10 ** 6,
+                 dtype=dtype, batch_size=gb, batch_mode="global", epochs=10 ** 6,
                  sync_mode="iter" if algo == "decent" else args.sync_mode,
                  horizon=args.horizon, topk_percent=args.topk,
-                 overlap_push=(args.overlap == "on") or (args.overlap == "auto" and N >= 2 and backend == "p2p"),
-                 channels_last=not args.no_channels_last, cuda_graph=not args.no_graph,
+                 overlap_push=tri[args.overlap] if backend == "p2p" else False,
+                 channels_last=False if args.no_channels_last else None,
+                 cuda_graph=False if args.no_graph else None,
                  ce_push=args.ce_push, double_buffer=args.double_buffer,
-                 train_samples=n_train, test_samples=256, quiet=True, augment=True)
-    src = synthetic_source("cifar10", n_train).pin()
+                 train_samples=len(src), test_samples=256, quiet=True, augment=True)
     tr = Trainer(cfg, env, train_source=src)
+    cfg = tr.cfg                      # with the auto switches resolved for this device / world size
     dev = env.device
     table = tr.arena.table
-
     # ---------------- device-timed: inputs resident on the GPU (a rotating pool of batches) -------
     pool = []
     it = iter(tr.loader)
@@ -116,26 +113,30 @@ def main():
         tr.train_step(*pool[i % len(pool)])
     torch.cuda.synchronize()
     barrier(env)
-    sampler = ClockSampler(dev.index or 0, 25).start() if env.rank == 0 else None
+    sampler = NvmlClockSampler(dev.index or 0, 2.0).start() if (env.rank == 0 and sample_clocks) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(env)
     torch.cuda.synchronize()
+    own0 = tr.own_launches_total
+    if sampler is not None:
+        sampler.mark_begin()
     e0.record()
     for i in range(args.steps):
         tr.train_step(*pool[i % len(pool)])
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
+    own_launches = tr.own_launches_total - own0
     barrier(env)
     ms = max_over_ranks(e0.elapsed_time(e1), env)
-    clocks = sampler.stop() if sampler is not None else None
     tr.backend.check_status() if hasattr(tr.backend, "check_status") else None
-    ms_per_step = ms / args.steps
-    value = gb * args.steps / (ms / 1e3)
-    loss_dev = float(tr.last_loss)
+    res = {"dtype": dtype, "ms_per_step": ms / args.steps, "value": gb * args.steps / (ms / 1e3),
+           "loss": float(tr.last_loss), "clocks": clocks, "gpu_launches": int(own_launches),
+           "own_kernels_per_step": dict(tr.own_launches_per_step), "cfg": cfg, "gb": gb, "per_rank": per_rank,
+           "table": table, "algo": algo, "backend": backend}
 
     # ---------------- end to end through the public API: H2D every step + D2H loss every step ----
-    e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         it = iter(tr.loader)
         for _ in range(args.warmup):
             x, y = next(it)
@@ -173,7 +174,6 @@ def main():
             d2h += loss.element_size()
         evs[(args.steps - 1) & 1].synchronize()
         losses.append(float(host_loss[(args.steps - 1) & 1][0]))
-        lv = losses[-1]
         assert len(losses) == args.steps
         e1.record()
         torch.cuda.synchronize()
@@ -181,16 +181,16 @@ def main():
         barrier(env)
         ms2 = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3), env)
         c, h, w = src.sample_shape
-        e2e = {"value": gb * args.steps / (ms2 / 1e3), "unit": "images/s",
-               "ms_per_step": ms2 / args.steps,
-               "h2d_bytes_per_step": int(per_rank * (c * h * w + 8) * N),
-               "d2h_bytes_per_step": int(d2h / args.steps * N),
-               "result_read": "every step, async D2H into pinned memory, consumed one step later",
-               "host_ms": {"loader": tl / args.steps * 1e3, "launch": tt / args.steps * 1e3,
-                           "result_wait": ti / args.steps * 1e3},
-               "last_loss": lv}
+        res["e2e"] = {"value": gb * args.steps / (ms2 / 1e3), "unit": "images/s",
+                      "ms_per_step": ms2 / args.steps,
+                      "h2d_bytes_per_step": int(per_rank * (c * h * w + 8) * N),
+                      "d2h_bytes_per_step": int(d2h / args.steps * N),
+                      "result_read": "every step, async D2H into pinned memory, consumed one step later",
+                      "host_ms": {"loader": tl / args.steps * 1e3, "launch": tt / args.steps * 1e3,
+                                  "result_wait": ti / args.steps * 1e3},
+                      "last_loss": losses[-1]}
 
-    if args.profile and env.rank == 0:
+    if args.profile and env.rank == 0 and want_e2e:
         from torch.profiler import ProfilerActivity, profile
         it = iter(tr.loader)
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -209,50 +209,83 @@ def main():
     bytes_all = sum_over_ranks(bytes_rank, env)
     events_all = sum_over_ranks(be.num_events(), env)
     dense_msgs = 2 * table.n_tensors * total_steps * N
-    push_bytes_step = bytes_rank / max(1, total_steps)
-    # kernels of THIS repo launched per step inside the timed region: the exchange/update kernel(s) plus
-    # the fused BatchNorm kernels (2 forward + 2 backward per BN layer when the bf16 NHWC path is active)
-    from eventgrad_b200.ops.bn_act import FusedBNAct
-    n_bn = sum(1 for m in tr.model.modules() if isinstance(m, FusedBNAct))
-    bn_native = args.dtype == "bf16" and cfg.channels_last and os.environ.get("EGB_FUSED_BN", "1") != "0"
-    step_kernels = {"decent": 1, "event": 1, "cent": 1, "spevent": 11}[algo] \
-        + (1 if (cfg.overlap_push and algo in ("decent", "event") and N > 1) else 0)
-    kern_per_step = (step_kernels if args.impl == "ours" else 0) + (4 * n_bn if bn_native else 0)
+    res["comm"] = {"bytes_pushed_per_step_per_gpu": bytes_rank / max(1, total_steps),
+                   "events_total": events_all, "dense_messages": dense_msgs,
+                   "messages_saved": (1.0 - events_all / dense_msgs)
+                   if (algo in ("event", "spevent") and dense_msgs and N > 1) else 0.0,
+                   "bytes_pushed_total": bytes_all,
+                   "wire_dedup_2rank_ring": bool(getattr(be, "wire_dedup", False))}
+    res["dbuf"] = bool(getattr(be, "dbuf", False))
+    res["nvls"] = bool(getattr(be, "nvls", False))
+    tr.close()
+    del tr
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    from eventgrad_b200.data import synthetic_source
+    from eventgrad_b200.utils.dist import init_distributed, shutdown
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "error": "bench.py needs a CUDA device (run it through gpurun / on the B200 box)"}))
+        return 2
+    env = init_distributed("cuda")
+    N = env.world
+    if N != args.gpus and env.rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={N}", file=sys.stderr)
+    gb = args.global_batch if args.scaling == "strong" else args.global_batch * N
+    n_train = max(max(1, gb // N) * N * 8, 4096)
+    src = synthetic_source("cifar10", n_train).pin()
+    r = measure(args, env, args.dtype, not args.no_e2e, src, True)
+    others = {}
+    for dt in [d for d in args.also.split(",") if d and d != args.dtype]:
+        o = measure(args, env, dt, False, src, False)
+        others[dt] = {"value": o["value"], "ms_per_step": o["ms_per_step"], "loss": o["loss"],
+                      "gpu_launches": o["gpu_launches"], "timing": "device-timed (CUDA events), same config otherwise"}
+    cfg, table, algo = r["cfg"], r["table"], r["algo"]
     out = {
         "metric": "images/sec, CIFAR-10 ResNet (reference topology) D-PSGD ring gossip training step",
-        "value": value, "unit": "images/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+        "value": r["value"], "unit": "images/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "impl": args.impl,
         "config": {"model": f"{args.model}-ref(12 BasicBlocks, 86 tensors, {table.n_elems} params)"
                             if args.model == "resnet18" else args.model,
-                   "global_batch": gb, "per_gpu_batch": per_rank, "seq_len": None, "image": "3x32x32",
+                   "global_batch": r["gb"], "per_gpu_batch": r["per_rank"], "seq_len": None, "image": "3x32x32",
                    "parallelism": f"dp{N}-ring-gossip" if algo != "cent" else f"dp{N}-allreduce",
-                   "algorithm": args.algo, "backend": backend, "sync_mode": cfg.sync_mode, "overlap_push": cfg.overlap_push,
-                   "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": cfg.cuda_graph,
-                   "channels_last": cfg.channels_last,
-                   # opt-in experimental paths active in this run (all off = the validated default code)
-                   "experimental": {k: v for k, v in {
-                       "bn_v2": os.environ.get("EGB_BN_V2") == "1", "bn_cluster": os.environ.get("EGB_BN_CLUSTER") == "1",
-                       "conv_split_bwd": os.environ.get("EGB_CONV_SPLIT_BWD") == "1",
-                       "nvls": os.environ.get("EGB_NVLS") == "1", "ce_push": bool(cfg.ce_push),
-                       "double_buffer": bool(cfg.double_buffer)}.items() if v},
+                   "algorithm": args.algo, "backend": r["backend"], "sync_mode": cfg.sync_mode,
+                   "precision": {"fp32": "IEEE fp32 forward/backward, TF32 off (reference precision)",
+                                 "tf32": "TF32 tensor-core convolutions / GEMMs", "bf16": "bf16 autocast"}[args.dtype]
+                                + "; parameters, exchange, average and SGD are fp32 in every mode",
+                   "overlap_push": bool(cfg.overlap_push), "double_buffer": r["dbuf"], "ce_push": bool(cfg.ce_push),
+                   "nvls": r["nvls"],
+                   "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": bool(cfg.cuda_graph),
+                   "channels_last": bool(cfg.channels_last),
+                   "defaults": "execution switches are the Trainer's defaults for this device (same as the CLI)"
+                               if (args.overlap == "auto" and not args.no_graph and not args.no_channels_last
+                                   and not args.ce_push and args.double_buffer is None) else "overridden by flags",
                    "l2_policy": "per-step working set (theta,grad,mom,2 inboxes = "
                                 f"{5 * table.n_padded * 4 / 1e6:.0f} MB + activations) exceeds the 126 MB L2; "
                                 "no explicit flush"},
-        "gpu_launches": int(kern_per_step * args.steps),
-        "own_kernels_per_step": {"exchange_update": step_kernels if args.impl == "ours" else 0,
-                                 "fused_batchnorm": 4 * n_bn if bn_native else 0},
-        "comm": {"bytes_pushed_per_step_per_gpu": push_bytes_step,
-                 "events_total": events_all, "dense_messages": dense_msgs,
-                 "messages_saved": (1.0 - events_all / dense_msgs) if (algo in ("event", "spevent") and dense_msgs and N > 1) else 0.0,
-                 "bytes_pushed_total": bytes_all},
-        "loss": loss_dev,
+        "gpu_launches": r["gpu_launches"],
+        "gpu_launches_how": "counted by the extension's launchers (csrc/api.h eg_count_launch) inside the timed "
+                            "region on rank 0; kernels replayed from the step's CUDA graph are counted from the capture",
+        "own_kernels_per_step": r["own_kernels_per_step"],
+        "comm": r["comm"],
+        "loss": r["loss"],
     }
-    if clocks is not None:
-        out["clocks"] = clocks
-    if e2e is not None:
-        out["e2e"] = e2e
+    if r["clocks"] is not None:
+        out["clocks"] = r["clocks"]
+    if "e2e" in r:
+        out["e2e"] = r["e2e"]
+    if others:
+        out["other_dtypes"] = others
     if env.rank == 0:
         line = json.dumps(out)
         print(line, flush=True)
@@ -260,7 +293,6 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
             with open(args.out, "w") as f:
                 f.write(line + "\n")
-    tr.close()
     shutdown()
     return 0
 

@@ -20,7 +20,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                            "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-CU_SOURCES = ["gossip.cu", "gossip_dbuf.cu", "ce_push.cu", "allreduce.cu", "allreduce_nvls.cu", "sparse.cu", "augment.cu", "ipc.cu", "bn_act.cu", "bn_act_v2.cu", "bn_act_cluster.cu", "linear_tc.cu", "linear_tc_tma.cu"]
+CU_SOURCES = ["gossip.cu", "gossip_dbuf.cu", "ce_push.cu", "allreduce.cu", "allreduce_nvls.cu", "sparse.cu", "augment.cu", "ipc.cu", "bn_act.cu", "linear_tc_tma.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 HEADERS = ["api.h", "common.cuh", "bn_common.cuh", "host_loader.h"]
 
@@ -56,7 +56,19 @@ def _run(cmd, log):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile what is stale and link the extension.  Safe under torchrun: ranks serialise on a file lock (the first
+    one builds, the others find everything fresh) and the .so is linked to a temp name and renamed into place."""
+    import fcntl
     os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     nvcc = os.path.join(CUDA_HOME, "bin", "nvcc")
     if not os.path.exists(nvcc):
         nvcc = shutil.which("nvcc") or nvcc
@@ -87,11 +99,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     out = so_path()
     if jobs or force or not os.path.exists(out):
         rdirs = _cudart_dirs()
-        link = ["g++", "-shared", "-o", out] + objs
+        tmp = out + f".tmp{os.getpid()}"
+        link = ["g++", "-shared", "-o", tmp] + objs
         for d in rdirs:
             link += ["-L", d, f"-Wl,-rpath,{d}"]
         link += ["-l:libcudart.so.12", "-lpthread"]
         _run(link, log)
+        os.replace(tmp, out)
     with open(os.path.join(BUILD, "build.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

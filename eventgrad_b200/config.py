@@ -50,14 +50,17 @@ class TrainConfig:
     final_divide_all: bool = True    # reference divides on rank 0 only (Q5)
     grad_table: bool = True          # p2p gossip: step kernel reads autograd's gradients in place (+ bf16
                                      # shadow weights under dtype=bf16) instead of an fp32 grad arena
-    overlap_push: bool = False       # p2p: launch the push half of the step on a side stream so it
-                                     # overlaps forward/backward (False = single fused kernel)
+    overlap_push: Optional[bool] = None   # p2p: launch the push half of the step on a side stream so it overlaps
+                                     # forward/backward (False = single fused kernel).  None = auto: on for
+                                     # decent/event on >= 2 GPUs (measured faster at N=2/4/8, profiles/README.md)
     spevent_fresh_replicas: bool = False   # reference quirk Q8: prev/left/right replicas of spevent are three
                                      # MORE randomly initialised networks (spevent.cpp:123-136) instead of theta_0
-    ce_push: bool = False            # EXPERIMENTAL (decent + overlap_push): the push half of the split step is two
-                                     # copy-engine memcpys instead of an SM kernel (csrc/ce_push.cu)
-    double_buffer: bool = False      # EXPERIMENTAL (decent, p2p, iter-sync, fused step): two inbox slots,
-                                     # no WAR ack (csrc/gossip_dbuf.cu); not yet run on hardware
+    ce_push: bool = False            # decent + overlap_push: the push half of the split step is copy-engine memcpys
+                                     # instead of an SM kernel (csrc/ce_push.cu)
+    double_buffer: Optional[bool] = None   # decent, p2p, iter-sync, fused (non-split) step: two inbox slots and no
+                                     # WAR ack (csrc/gossip_dbuf.cu).  None = on where it applies
+    peer_timeout_s: float = 30.0     # bound of every device-side peer wait (sticky status instead of a hang);
+                                     # EGB_PEER_TIMEOUT_S overrides
     # ---- data --------------------------------------------------------------
     data: str = "synthetic"          # synthetic | path to dataset root
     sampler: str = "random"          # random | sequential
@@ -69,8 +72,8 @@ class TrainConfig:
     # ---- execution ---------------------------------------------------------
     device: str = "auto"             # auto | cuda | cpu
     dtype: str = "fp32"              # fp32 | tf32 | bf16 (compute dtype; arena is fp32)
-    channels_last: bool = False
-    cuda_graph: bool = False
+    channels_last: Optional[bool] = None   # None = auto: NHWC activations/weights + fused BN kernels on CUDA
+    cuda_graph: Optional[bool] = None      # None = auto: whole-step CUDA graph on CUDA
     max_steps: int = 0               # >0: stop after this many steps (tests / bench)
     cudnn_benchmark: bool = True     # cuDNN autotune: best steady state, but every new conv shape costs a
                                      # one-time search (seconds; it also hits the partial last batch)
@@ -102,6 +105,21 @@ class TrainConfig:
         if self.dtype not in ("fp32", "tf32", "bf16"):
             raise ValueError("dtype must be fp32|tf32|bf16")
         return self
+
+    def resolved(self, device_type: str, world: int) -> "TrainConfig":
+        """Fill the auto (None) execution switches for the device the job actually runs on: on a GPU the fast path
+        (NHWC + fused BN kernels, whole-step CUDA graph, pushes overlapped with backward) IS the default path."""
+        cuda = device_type == "cuda"
+        p2p = self.backend == "p2p" or (self.backend == "auto" and cuda)
+        kw = {}
+        if self.channels_last is None:
+            kw["channels_last"] = cuda
+        if self.cuda_graph is None:
+            kw["cuda_graph"] = cuda
+        if self.overlap_push is None:
+            kw["overlap_push"] = bool(cuda and p2p and world >= 2 and self.algo in ("decent", "event")
+                                      and not bool(self.double_buffer))
+        return dataclasses.replace(self, **kw) if kw else self
 
     def replace(self, **kw) -> "TrainConfig":
         return dataclasses.replace(self, **kw)
@@ -151,8 +169,10 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--initial-comm-passes", type=int, default=None)
     p.add_argument("--backend", default=None, choices=["auto", "p2p", "nccl", "gloo", "refport"])
     p.add_argument("--sync-mode", default=None, choices=["iter", "async"])
-    p.add_argument("--overlap-push", action="store_true", default=None)
-    p.add_argument("--double-buffer", action="store_true", default=None)
+    p.add_argument("--overlap-push", action=argparse.BooleanOptionalAction, default=None,
+                   help="default: on for decent/event on >= 2 GPUs")
+    p.add_argument("--double-buffer", action=argparse.BooleanOptionalAction, default=None)
+    p.add_argument("--peer-timeout-s", type=float, default=None)
     p.add_argument("--ce-push", action="store_true", default=None)
     p.add_argument("--fresh-replicas", dest="spevent_fresh_replicas", action="store_true", default=None,
                    help="spevent: initialise prev/left/right replicas like the reference (three more random nets)")
@@ -165,8 +185,8 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--test-samples", type=int, default=None)
     p.add_argument("--device", default=None, choices=["auto", "cuda", "cpu"])
     p.add_argument("--dtype", default=None, choices=["fp32", "tf32", "bf16"])
-    p.add_argument("--channels-last", action="store_true", default=None)
-    p.add_argument("--cuda-graph", action="store_true", default=None)
+    p.add_argument("--channels-last", action=argparse.BooleanOptionalAction, default=None, help="default: on for CUDA")
+    p.add_argument("--cuda-graph", action=argparse.BooleanOptionalAction, default=None, help="default: on for CUDA")
     p.add_argument("--no-cudnn-benchmark", dest="cudnn_benchmark", action="store_false", default=None)
     p.add_argument("--max-steps", type=int, default=None)
     p.add_argument("--log-dir", default=None)

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) EG_AR_SYM(allreduce_kernel)(con
 
 #ifndef EG_NVLS
 cudaError_t launch_allreduce(const AllReduceParams& p, int grid, cudaStream_t s) {
+  eg_count_launch(EG_FAM_ALLREDUCE, 1);
   if (p.mode == 1 && p.mu != 0.f && p.mom != nullptr)
     allreduce_kernel<true><<<grid, EG_THREADS, 0, s>>>(p);
   else
@@ -170,6 +171,7 @@ cudaError_t launch_allreduce(const AllReduceParams& p, int grid, cudaStream_t s)
 #else
 // two-shot only; p.mc_local = multicast mapping of `local` (torch symmetric memory, see parallel/window.py)
 cudaError_t launch_allreduce_nvls(const AllReduceParams& p, int grid, cudaStream_t s) {
+  eg_count_launch(EG_FAM_ALLREDUCE, 1);
   if (!p.two_shot || p.mc_local == nullptr) return cudaErrorInvalidValue;
   if (p.mode == 1 && p.mu != 0.f && p.mom != nullptr)
     allreduce_kernel_nvls<true><<<grid, EG_THREADS, 0, s>>>(p);

@@ -10,6 +10,13 @@
 
 namespace egb {
 
+// ------------------------------------------------------------------ launch accounting (host)
+// Every launcher of this extension counts the kernels it enqueues (per family), so "how many of OUR kernels ran
+// in this region" is counted, not derived from a formula (bench.py `gpu_launches`; during CUDA-graph capture the
+// Trainer records the per-step delta and multiplies by the replays).
+enum { EG_FAM_GOSSIP = 0, EG_FAM_ALLREDUCE, EG_FAM_SPARSE, EG_FAM_BN, EG_FAM_LINEAR, EG_FAM_DATA, EG_FAM_N };
+void eg_count_launch(int family, int n);
+
 // ------------------------------------------------------------------ tensor table (device)
 struct TableDev {
   const int* tile_tensor;   // [n_tiles]  tile -> parameter tensor
@@ -187,14 +194,16 @@ cudaError_t launch_decode_augment(const uint8_t* in, void* out, const int* oy, c
                                   float mean, float inv_std, int out_bf16, int nhwc, cudaStream_t s);
 
 // ------------------------------------------------------------------ fused BatchNorm(+add)(+ReLU)
-// NHWC bf16 activations [M = N*H*W, C], fp32 statistics / affine parameters (csrc/bn_act.cu).
+// NHWC activations [M = N*H*W, C] in fp32 (reference precision) or bf16, fp32 statistics / affine parameters
+// (csrc/bn_act.cu).
 struct BnParams {
-  const __nv_bfloat16* x;     // BN input (conv output)
-  const __nv_bfloat16* res;   // optional residual added before the activation
-  __nv_bfloat16* y;           // output (forward) / saved output for the ReLU mask (backward)
-  const __nv_bfloat16* dy;    // backward: grad wrt y
-  __nv_bfloat16* dx;          // backward: grad wrt x
-  __nv_bfloat16* dres;        // backward: grad wrt residual (optional)
+  const void* x;              // BN input (conv output)
+  const void* res;            // optional residual added before the activation
+  void* y;                    // output (forward) / saved output for the ReLU mask (backward)
+  const void* dy;             // backward: grad wrt y
+  void* dx;                   // backward: grad wrt x
+  void* dres;                 // backward: grad wrt residual (optional)
+  int fp32;                   // 1: activations are float, 0: __nv_bfloat16
   const float* gamma;
   const float* beta;
   float* mean;                // saved batch mean   [C]
@@ -220,21 +229,8 @@ int bn_partial_rows(int sm_count);
 // which: 0 training forward, 1 apply only (eval), 2 backward
 cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s);
 
-// v2 (experimental, csrc/bn_act_v2.cu): the training forward also emits one ReLU bit per element and the
-// backward reads that mask instead of y.  mask: [C/64][M][8] bytes, required when relu != 0.
-struct BnParamsV2 {
-  BnParams b;
-  unsigned char* mask;
-};
-// which: 0 training forward, 2 backward
-cudaError_t launch_bn_v2(const BnParamsV2& p, int which, int sm_count, cudaStream_t s);
-// single-launch thread-block-cluster / DSMEM variant (experimental, csrc/bn_act_cluster.cu); *taken = 0 when the
-// slice does not fit one cluster's shared memory -- the caller then uses launch_bn_v2
-cudaError_t launch_bn_cluster(const BnParamsV2& p, int which, cudaStream_t s, int* taken);
-void bn_cluster_plan(long long M, int which, int* cs, long long* rows_per_cta, size_t* smem_bytes);
-
 // ------------------------------------------------------------------ tcgen05 fused Linear(+bias)(+ReLU)
-// Y[M,N] = act(X[M,K] * W[N,K]^T + b): bf16 operands, fp32 accumulation in TMEM (csrc/linear_tc.cu).
+// Y[M,N] = act(X[M,K] * W[N,K]^T + b): bf16 operands, fp32 accumulation in TMEM (csrc/linear_tc_tma.cu).
 struct LinearParams {
   const __nv_bfloat16* x;   // [M, K] row-major
   const __nv_bfloat16* w;   // [N, K] row-major (nn.Linear weight layout)
@@ -244,8 +240,7 @@ struct LinearParams {
   int relu;
   int out_bf16;
 };
-cudaError_t launch_linear_tc(const LinearParams& p, cudaStream_t s);
-// EXPERIMENTAL (not yet run on hardware): TMA + SWIZZLE_128B + persistent CTAs, csrc/linear_tc_tma.cu
+// TMA + SWIZZLE_128B + persistent CTAs (one per SM) + double-buffered TMEM accumulator
 cudaError_t launch_linear_tc_tma(const LinearParams& p, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------ IPC window runtime

@@ -45,6 +45,7 @@ cudaError_t launch_decode_augment(const uint8_t* in, void* out, const int* oy, c
   const int n = B * H * W;
   if (n == 0) return cudaSuccess;
   const int grid = (n + 255) / 256;
+  eg_count_launch(EG_FAM_DATA, 1);
 #define EG_AUG(BF, NH) \
   decode_augment_kernel<BF, NH><<<grid, 256, 0, s>>>(in, out, oy, ox, flip, B, C, H, W, pad, scale, mean, inv_std)
   if (out_bf16) {

@@ -90,6 +90,7 @@ static const std::unordered_map<std::string, Setter<BnParams>> kBn = {
     PTRF(BnParams, dgamma), PTRF(BnParams, dbeta), PTRF(BnParams, partial), PTRF(BnParams, ticket),
     PTRF(BnParams, flag), PTRF(BnParams, epoch), PTRF(BnParams, status), NUMF(BnParams, fused_ok),
     NUMF(BnParams, M), NUMF(BnParams, C), NUMF(BnParams, eps), NUMF(BnParams, momentum), NUMF(BnParams, relu),
+    NUMF(BnParams, fp32),
 };
 
 template <class S>
@@ -123,6 +124,15 @@ static void bind_params(py::module_& m, const char* name, const std::unordered_m
 }
 
 static cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- launch accounting (api.h): relaxed atomics, one counter per kernel family
+#include <atomic>
+static std::atomic<long long> g_launches[egb::EG_FAM_N];
+namespace egb {
+void eg_count_launch(int family, int n) {
+  if (family >= 0 && family < EG_FAM_N) g_launches[family].fetch_add(n, std::memory_order_relaxed);
+}
+}  // namespace egb
 
 PYBIND11_MODULE(_C, m) {
   m.doc() = "eventgrad_b200 sm_100a kernels";
@@ -164,6 +174,17 @@ PYBIND11_MODULE(_C, m) {
   m.def("sparse_apply", [](const SparseParams& p, int grid, uintptr_t s) {
     check(launch_sparse_apply(p, grid, S(s)), "sparse_apply");
   });
+  m.def("launch_counts", []() {
+    py::dict d;
+    const char* names[egb::EG_FAM_N] = {"gossip", "allreduce", "sparse", "bn", "linear", "data"};
+    for (int i = 0; i < egb::EG_FAM_N; ++i) d[names[i]] = g_launches[i].load(std::memory_order_relaxed);
+    return d;
+  });
+  m.def("launch_count", []() {
+    long long t = 0;
+    for (int i = 0; i < egb::EG_FAM_N; ++i) t += g_launches[i].load(std::memory_order_relaxed);
+    return t;
+  });
   m.def("bn_partial_rows", &bn_partial_rows);
   m.def("bn_launch", [](const BnParams& p, int which, int sm_count, uintptr_t s) {
     check(launch_bn(p, which, sm_count, S(s)), "bn_launch");
@@ -174,12 +195,14 @@ PYBIND11_MODULE(_C, m) {
   m.def("bn_forward", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t gamma, uintptr_t beta, uintptr_t mean,
                          uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt, uintptr_t partial,
                          uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
-                         float eps, float momentum, int relu, int training, int fused_ok, int sm_count, uintptr_t s) {
+                         float eps, float momentum, int relu, int training, int fused_ok, int sm_count, int fp32,
+                         uintptr_t s) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
-    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-    p.res = reinterpret_cast<const __nv_bfloat16*>(res);
-    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.fp32 = fp32;
+    p.x = reinterpret_cast<const void*>(x);
+    p.res = reinterpret_cast<const void*>(res);
+    p.y = reinterpret_cast<void*>(y);
     p.gamma = reinterpret_cast<const float*>(gamma);
     p.beta = reinterpret_cast<const float*>(beta);
     p.mean = reinterpret_cast<float*>(mean);
@@ -198,14 +221,15 @@ PYBIND11_MODULE(_C, m) {
   m.def("bn_backward", [](uintptr_t x, uintptr_t y, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
                           uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
                           uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
-                          int relu, int fused_ok, int sm_count, uintptr_t s) {
+                          int relu, int fused_ok, int sm_count, int fp32, uintptr_t s) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
-    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-    p.y = reinterpret_cast<__nv_bfloat16*>(y);
-    p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
-    p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
-    p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
+    p.fp32 = fp32;
+    p.x = reinterpret_cast<const void*>(x);
+    p.y = reinterpret_cast<void*>(y);
+    p.dy = reinterpret_cast<const void*>(dy);
+    p.dx = reinterpret_cast<void*>(dx);
+    p.dres = reinterpret_cast<void*>(dres);
     p.gamma = reinterpret_cast<const float*>(gamma);
     p.mean = reinterpret_cast<float*>(mean);
     p.invstd = reinterpret_cast<float*>(invstd);
@@ -219,78 +243,7 @@ PYBIND11_MODULE(_C, m) {
     p.M = M; p.C = C; p.relu = relu; p.fused_ok = fused_ok;
     check(launch_bn(p, 2, sm_count, S(s)), "bn_backward");
   });
-  // experimental v2 (ReLU bit mask): same positional layout + the mask address
-  m.def("bn_forward_v2", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, uintptr_t gamma, uintptr_t beta,
-                            uintptr_t mean, uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt,
-                            uintptr_t partial, uintptr_t ticket, uintptr_t status, long long M, int C, float eps,
-                            float momentum, int relu, int sm_count, int cluster, uintptr_t s) {
-    BnParamsV2 pp;
-    std::memset(&pp, 0, sizeof(pp));
-    BnParams& p = pp.b;
-    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-    p.res = reinterpret_cast<const __nv_bfloat16*>(res);
-    p.y = reinterpret_cast<__nv_bfloat16*>(y);
-    pp.mask = reinterpret_cast<unsigned char*>(mask);
-    p.gamma = reinterpret_cast<const float*>(gamma);
-    p.beta = reinterpret_cast<const float*>(beta);
-    p.mean = reinterpret_cast<float*>(mean);
-    p.invstd = reinterpret_cast<float*>(invstd);
-    p.run_mean = reinterpret_cast<float*>(run_mean);
-    p.run_var = reinterpret_cast<float*>(run_var);
-    p.nbt = reinterpret_cast<long long*>(nbt);
-    p.partial = reinterpret_cast<float*>(partial);
-    p.ticket = reinterpret_cast<unsigned int*>(ticket);
-    p.status = reinterpret_cast<int*>(status);
-    p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu;
-    int taken = 0;
-    if (cluster) check(launch_bn_cluster(pp, 0, S(s), &taken), "bn_forward_cluster");
-    if (!taken) check(launch_bn_v2(pp, 0, sm_count, S(s)), "bn_forward_v2");
-    return taken;
-  });
-  m.def("bn_cluster_plan", [](long long M, int which) {
-    int cs = 0;
-    long long rows = 0;
-    size_t smem = 0;
-    bn_cluster_plan(M, which, &cs, &rows, &smem);
-    return py::make_tuple(cs, rows, smem);
-  });
-  m.def("bn_backward_v2", [](uintptr_t x, uintptr_t mask, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
-                             uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
-                             uintptr_t ticket, uintptr_t status, long long M, int C, int relu, int sm_count,
-                             int cluster, uintptr_t s) {
-    BnParamsV2 pp;
-    std::memset(&pp, 0, sizeof(pp));
-    BnParams& p = pp.b;
-    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-    pp.mask = reinterpret_cast<unsigned char*>(mask);
-    p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
-    p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
-    p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
-    p.gamma = reinterpret_cast<const float*>(gamma);
-    p.mean = reinterpret_cast<float*>(mean);
-    p.invstd = reinterpret_cast<float*>(invstd);
-    p.dgamma = reinterpret_cast<float*>(dgamma);
-    p.dbeta = reinterpret_cast<float*>(dbeta);
-    p.partial = reinterpret_cast<float*>(partial);
-    p.ticket = reinterpret_cast<unsigned int*>(ticket);
-    p.status = reinterpret_cast<int*>(status);
-    p.M = M; p.C = C; p.relu = relu;
-    int taken = 0;
-    if (cluster) check(launch_bn_cluster(pp, 2, S(s), &taken), "bn_backward_cluster");
-    if (!taken) check(launch_bn_v2(pp, 2, sm_count, S(s)), "bn_backward_v2");
-    return taken;
-  });
   m.def("linear_tc", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int M, int N, int K, int relu,
-                        int out_bf16, uintptr_t s) {
-    LinearParams p;
-    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-    p.w = reinterpret_cast<const __nv_bfloat16*>(w);
-    p.bias = reinterpret_cast<const float*>(bias);
-    p.y = reinterpret_cast<void*>(y);
-    p.M = M; p.N = N; p.K = K; p.relu = relu; p.out_bf16 = out_bf16;
-    check(launch_linear_tc(p, S(s)), "linear_tc");
-  });
-  m.def("linear_tc_tma", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int M, int N, int K, int relu,
                             int out_bf16, int sm_count, uintptr_t s) {
     LinearParams p;
     p.x = reinterpret_cast<const __nv_bfloat16*>(x);
@@ -298,7 +251,7 @@ PYBIND11_MODULE(_C, m) {
     p.bias = reinterpret_cast<const float*>(bias);
     p.y = reinterpret_cast<void*>(y);
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.out_bf16 = out_bf16;
-    check(launch_linear_tc_tma(p, sm_count, S(s)), "linear_tc_tma (experimental)");
+    check(launch_linear_tc_tma(p, sm_count, S(s)), "linear_tc");
   });
   m.def("decode_augment",
         [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,

@@ -1,5 +1,6 @@
 // eventgrad_b200 -- fused BatchNorm2d (+ residual add) (+ ReLU), training forward + backward,
-// channels-last bf16 activations, fp32 statistics/parameters.  sm_100a.
+// channels-last activations in fp32 (the reference's precision, event.cpp:279) or bf16 -- every kernel is a
+// template over the element type -- fp32 statistics/parameters.  sm_100a.
 //
 // Why: a launch-level profile of the flagship step (CIFAR ResNet, bf16 autocast, see profiles/)
 // shows ATen's batch-norm + elementwise kernels taking ~2/3 of the GPU time while the tcgen05
@@ -22,16 +23,33 @@
 
 namespace egb {
 
+// typed views of the type-erased BnParams pointers
+// loads in flight per thread in the stats loop: 8 x 16 B (bf16) / 4 x 32 B (fp32)
+#define BN_STATS_UNROLL(T) (sizeof(T) == 2 ? 8 : 4)
+#define BN_APPLY_UNROLL(T) (sizeof(T) == 2 ? 4 : 2)
+#define BN_RED_UNROLL(T) (sizeof(T) == 2 ? 3 : 2)
+#define BN_DX_UNROLL(T) (sizeof(T) == 2 ? 2 : 1)
+#define BN_PTRS(T)                                                              \
+  const T* __restrict__ px = static_cast<const T*>(p.x);                        \
+  const T* __restrict__ pres = static_cast<const T*>(p.res);                    \
+  T* __restrict__ py = static_cast<T*>(p.y);                                    \
+  const T* __restrict__ pdy = static_cast<const T*>(p.dy);                      \
+  T* __restrict__ pdx = static_cast<T*>(p.dx);                                  \
+  T* __restrict__ pdres = static_cast<T*>(p.dres);                              \
+  (void)px; (void)pres; (void)py; (void)pdy; (void)pdx; (void)pdres;
+
 // ===========================================================================================
 // FUSED forward: stats + normalise (+res)(+relu) in one launch, x read once
 // ===========================================================================================
+template <typename T>
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnParams p) {
+  BN_PTRS(T)
   __shared__ __align__(16) float smem[BN_RPP * 128];
   const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const unsigned epoch = *reinterpret_cast<volatile unsigned int*>(p.epoch);
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
-  uint4 xr[BN_FWD_PASSES];
+  Raw8<T> xr[BN_FWD_PASSES];
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
@@ -39,11 +57,11 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnPar
 #pragma unroll
   for (int u = 0; u < BN_FWD_PASSES; ++u) {
     const long long row = row0 + u * BN_RPP;
-    xr[u] = (row < p.M) ? ldg16(p.x + row * p.C + coff) : make_uint4(0, 0, 0, 0);
+    if (row < p.M) xr[u] = ld8(px + row * p.C + coff); else zero8(xr[u]);
   }
 #pragma unroll
   for (int u = 0; u < BN_FWD_PASSES; ++u) {
-    const V8 x = unpack_bf16x8(xr[u]);                     // rows beyond M contribute exact zeros
+    const V8 x = unpack8(xr[u]);                           // rows beyond M contribute exact zeros
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       s[e] += x.v[e];
@@ -74,28 +92,32 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const BnPar
     sc[e] = p.gamma[c] * is;
     sh[e] = p.beta[c] - mean * sc[e];
   }
-  const bool has_res = p.res != nullptr;
+  const bool has_res = pres != nullptr;
 #pragma unroll
   for (int u = 0; u < BN_FWD_PASSES; ++u) {
     const long long row = row0 + u * BN_RPP;
     if (row >= p.M) continue;
-    V8 x = unpack_bf16x8(xr[u]);
+    V8 x = unpack8(xr[u]);
     V8 r;
-    if (has_res) r = unpack_bf16x8(ldg16(p.res + row * p.C + coff));
+    if (has_res) r = unpack8(ld8(pres + row * p.C + coff));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = fmaf(x.v[e], sc[e], sh[e]);
       if (has_res) v += r.v[e];
       x.v[e] = p.relu ? fmaxf(v, 0.f) : v;
     }
-    stg16(p.y + row * p.C + coff, pack_bf16x8(x));
+    Raw8<T> o;
+    pack8(x, o);
+    st8(py + row * p.C + coff, o);
   }
 }
 
 // ===========================================================================================
 // FUSED backward: reduce + dx (+dres) in one launch
 // ===========================================================================================
+template <typename T>
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnParams p) {
+  BN_PTRS(T)
   __shared__ __align__(16) float smem[BN_RPP * 128];
   const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -108,27 +130,26 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnPar
     is[e] = p.invstd[slice * BN_SLICE + tx * 8 + e];
     s1[e] = s2[e] = 0.f;
   }
-  uint4 dzr[BN_BWD_PASSES], xr[BN_BWD_PASSES];
+  Raw8<T> dzr[BN_BWD_PASSES], xr[BN_BWD_PASSES];
   const long long row0 = (long long)rs * (BN_BWD_PASSES * BN_RPP) + ty;
 #pragma unroll
   for (int u = 0; u < BN_BWD_PASSES; ++u) {
     const long long row = row0 + u * BN_RPP;
     const bool ok = row < p.M;
-    uint4 d = ok ? ldg16(p.dy + row * p.C + coff) : make_uint4(0, 0, 0, 0);
-    xr[u] = ok ? ldg16(p.x + row * p.C + coff) : make_uint4(0, 0, 0, 0);
-    if (p.relu && ok) {                                     // dz = dy * (y > 0): fold the mask into dz now
-      const uint4 yy = ldg16(p.y + row * p.C + coff);
-      const unsigned short* ys = reinterpret_cast<const unsigned short*>(&yy);
-      unsigned short* ds = reinterpret_cast<unsigned short*>(&d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if ((ys[e] & 0x8000u) || (ys[e] & 0x7fffu) == 0u) ds[e] = 0;   // y <= 0 (bf16 sign / zero test)
+    Raw8<T> d;
+    if (ok) {
+      d = ld8(pdy + row * p.C + coff);
+      xr[u] = ld8(px + row * p.C + coff);
+      if (p.relu) mask_le0(d, ld8(py + row * p.C + coff));  // dz = dy * (y > 0): fold the mask into dz now
+    } else {
+      zero8(d);
+      zero8(xr[u]);
     }
     dzr[u] = d;
   }
 #pragma unroll
   for (int u = 0; u < BN_BWD_PASSES; ++u) {
-    const V8 dz = unpack_bf16x8(dzr[u]), x = unpack_bf16x8(xr[u]);
+    const V8 dz = unpack8(dzr[u]), x = unpack8(xr[u]);
     const bool ok = (row0 + u * BN_RPP) < p.M;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -164,24 +185,28 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const BnPar
     k1[e] = __ldcg(p.dbeta + c) * invM;
     k2[e] = __ldcg(p.dgamma + c) * invM;
   }
-  const bool want_dres = p.dres != nullptr;
+  const bool want_dres = pdres != nullptr;
 #pragma unroll
   for (int u = 0; u < BN_BWD_PASSES; ++u) {
     const long long row = row0 + u * BN_RPP;
     if (row >= p.M) continue;
-    const V8 dz = unpack_bf16x8(dzr[u]);
-    V8 x = unpack_bf16x8(xr[u]);
+    const V8 dz = unpack8(dzr[u]);
+    V8 x = unpack8(xr[u]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) x.v[e] = k0[e] * (dz.v[e] - k1[e] - (x.v[e] - mu[e]) * is[e] * k2[e]);
-    stg16(p.dx + row * p.C + coff, pack_bf16x8(x));
-    if (want_dres) stg16(p.dres + row * p.C + coff, dzr[u]);
+    Raw8<T> o;
+    pack8(x, o);
+    st8(pdx + row * p.C + coff, o);
+    if (want_dres) st8(pdres + row * p.C + coff, dzr[u]);
   }
 }
 
 // ===========================================================================================
 // SPLIT path (large tensors)
 // ===========================================================================================
+template <typename T>
 __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnParams p) {
+  BN_PTRS(T)
   __shared__ __align__(16) float smem[BN_RPP * 128];
   const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -191,13 +216,13 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnPar
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   const long long stride = (long long)RS * BN_RPP;
   long long row = (long long)rs * BN_RPP + ty;
-  for (; row + 7 * stride < p.M; row += 8 * stride) {
-    uint4 xr[8];
+  for (; row + (BN_STATS_UNROLL(T) - 1) * stride < p.M; row += BN_STATS_UNROLL(T) * stride) {
+    Raw8<T> xr[BN_STATS_UNROLL(T)];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) xr[u] = ldg16(p.x + (row + u * stride) * p.C + coff);
+    for (int u = 0; u < BN_STATS_UNROLL(T); ++u) xr[u] = ld8(px + (row + u * stride) * p.C + coff);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const V8 x = unpack_bf16x8(xr[u]);
+    for (int u = 0; u < BN_STATS_UNROLL(T); ++u) {
+      const V8 x = unpack8(xr[u]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         s[e] += x.v[e];
@@ -206,7 +231,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnPar
     }
   }
   for (; row < p.M; row += stride) {
-    const V8 x = unpack_bf16x8(ldg16(p.x + row * p.C + coff));
+    const V8 x = unpack8(ld8(px + row * p.C + coff));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       s[e] += x.v[e];
@@ -220,7 +245,9 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_stats_kernel(const BnPar
   finalize_stats(p, slice, tot);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_apply_kernel(const BnParams p) {
+  BN_PTRS(T)
   const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
@@ -232,36 +259,40 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_apply_kernel(const BnPar
     sh[e] = p.beta[c] - p.mean[c] * sc[e];
   }
   const long long stride = (long long)RS * BN_RPP;
-  const bool has_res = p.res != nullptr;
-  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += 4 * stride) {
-    uint4 xr[4], rr[4];
+  const bool has_res = pres != nullptr;
+  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += BN_APPLY_UNROLL(T) * stride) {
+    Raw8<T> xr[BN_APPLY_UNROLL(T)], rr[BN_APPLY_UNROLL(T)];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < BN_APPLY_UNROLL(T); ++u) {
       const long long r2 = row + u * stride;
       if (r2 < p.M) {
-        xr[u] = ldg16(p.x + r2 * p.C + coff);
-        if (has_res) rr[u] = ldg16(p.res + r2 * p.C + coff);
+        xr[u] = ld8(px + r2 * p.C + coff);
+        if (has_res) rr[u] = ld8(pres + r2 * p.C + coff);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < BN_APPLY_UNROLL(T); ++u) {
       const long long r2 = row + u * stride;
       if (r2 >= p.M) continue;
-      V8 x = unpack_bf16x8(xr[u]);
+      V8 x = unpack8(xr[u]);
       V8 r;
-      if (has_res) r = unpack_bf16x8(rr[u]);
+      if (has_res) r = unpack8(rr[u]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         float v = fmaf(x.v[e], sc[e], sh[e]);
         if (has_res) v += r.v[e];
         x.v[e] = p.relu ? fmaxf(v, 0.f) : v;
       }
-      stg16(p.y + r2 * p.C + coff, pack_bf16x8(x));
+      Raw8<T> o;
+      pack8(x, o);
+      st8(py + r2 * p.C + coff, o);
     }
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParams p) {
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_reduce_kernel(const BnParams p) {
+  BN_PTRS(T)
   __shared__ __align__(16) float smem[BN_RPP * 128];
   const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -274,23 +305,23 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParam
     s1[e] = s2[e] = 0.f;
   }
   const long long stride = (long long)RS * BN_RPP;
-  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += 3 * stride) {
-    uint4 dr[3], xr[3], yr[3];
+  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += BN_RED_UNROLL(T) * stride) {
+    Raw8<T> dr[BN_RED_UNROLL(T)], xr[BN_RED_UNROLL(T)], yr[BN_RED_UNROLL(T)];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < BN_RED_UNROLL(T); ++u) {
       const long long r2 = row + u * stride;
       if (r2 < p.M) {
-        dr[u] = ldg16(p.dy + r2 * p.C + coff);
-        xr[u] = ldg16(p.x + r2 * p.C + coff);
-        if (p.relu) yr[u] = ldg16(p.y + r2 * p.C + coff);
+        dr[u] = ld8(pdy + r2 * p.C + coff);
+        xr[u] = ld8(px + r2 * p.C + coff);
+        if (p.relu) yr[u] = ld8(py + r2 * p.C + coff);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < BN_RED_UNROLL(T); ++u) {
       if (row + u * stride >= p.M) continue;
-      const V8 d = unpack_bf16x8(dr[u]), x = unpack_bf16x8(xr[u]);
+      const V8 d = unpack8(dr[u]), x = unpack8(xr[u]);
       V8 y;
-      if (p.relu) y = unpack_bf16x8(yr[u]);
+      if (p.relu) y = unpack8(yr[u]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dz = (p.relu && !(y.v[e] > 0.f)) ? 0.f : d.v[e];
@@ -309,7 +340,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnParam
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_dx_kernel(const BnParams p) {
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_dx_kernel(const BnParams p) {
+  BN_PTRS(T)
   const int slice = blockIdx.x, rs = blockIdx.y, RS = gridDim.y;   // slice fastest: CTAs scheduled together read adjacent 128 B of the same rows
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const size_t coff = (size_t)slice * BN_SLICE + tx * 8;
@@ -325,32 +358,37 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_dx_kernel(const BnParams p)
     k2[e] = p.dgamma[c] * invM;
   }
   const long long stride = (long long)RS * BN_RPP;
-  const bool want_dres = p.dres != nullptr;
-  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += 2 * stride) {
-    uint4 dr[2], xr[2], yr[2];
+  const bool want_dres = pdres != nullptr;
+  for (long long row = (long long)rs * BN_RPP + ty; row < p.M; row += BN_DX_UNROLL(T) * stride) {
+    Raw8<T> dr[BN_DX_UNROLL(T)], xr[BN_DX_UNROLL(T)], yr[BN_DX_UNROLL(T)];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < BN_DX_UNROLL(T); ++u) {
       const long long r2 = row + u * stride;
       if (r2 < p.M) {
-        dr[u] = ldg16(p.dy + r2 * p.C + coff);
-        xr[u] = ldg16(p.x + r2 * p.C + coff);
-        if (p.relu) yr[u] = ldg16(p.y + r2 * p.C + coff);
+        dr[u] = ld8(pdy + r2 * p.C + coff);
+        xr[u] = ld8(px + r2 * p.C + coff);
+        if (p.relu) yr[u] = ld8(py + r2 * p.C + coff);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < BN_DX_UNROLL(T); ++u) {
       const long long r2 = row + u * stride;
       if (r2 >= p.M) continue;
-      V8 d = unpack_bf16x8(dr[u]), x = unpack_bf16x8(xr[u]), y;
-      if (p.relu) y = unpack_bf16x8(yr[u]);
+      V8 d = unpack8(dr[u]), x = unpack8(xr[u]), y;
+      if (p.relu) y = unpack8(yr[u]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dz = (p.relu && !(y.v[e] > 0.f)) ? 0.f : d.v[e];
         d.v[e] = dz;
         x.v[e] = k0[e] * (dz - k1[e] - (x.v[e] - mu[e]) * is[e] * k2[e]);
       }
-      stg16(p.dx + r2 * p.C + coff, pack_bf16x8(x));
-      if (want_dres) stg16(p.dres + r2 * p.C + coff, pack_bf16x8(d));
+      Raw8<T> o;
+      pack8(x, o);
+      st8(pdx + r2 * p.C + coff, o);
+      if (want_dres) {
+        pack8(d, o);
+        st8(pdres + r2 * p.C + coff, o);
+      }
     }
   }
 }
@@ -361,7 +399,8 @@ int bn_partial_rows(int sm_count) { return sm_count * 4 + 64; }   // max total C
 static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
 // which: 0 training forward (stats [+ apply]), 1 apply only (eval), 2 backward
-cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s) {
+template <typename T>
+static cudaError_t launch_bn_t(const BnParams& p, int which, int sm_count, cudaStream_t s) {
   if (p.C % BN_SLICE != 0 || p.C / BN_SLICE > 32 || p.M < 1) return cudaErrorInvalidValue;
   const int slices = p.C / BN_SLICE;
   const long long passes = ceil_div(p.M, BN_RPP);
@@ -384,25 +423,34 @@ cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s
   if (which == 0) {
     const long long rs_f = ceil_div(passes, BN_FWD_PASSES);
     if (p.fused_ok && rs_f * slices <= max_ctas) {
-      bn_fwd_fused_kernel<<<dim3((unsigned)slices, (unsigned)rs_f), BN_THREADS, 0, s>>>(p);
+      eg_count_launch(EG_FAM_BN, 1);
+      bn_fwd_fused_kernel<T><<<dim3((unsigned)slices, (unsigned)rs_f), BN_THREADS, 0, s>>>(p);
     } else {
-      bn_fwd_stats_kernel<<<red_grid(), BN_THREADS, 0, s>>>(p);
-      bn_fwd_apply_kernel<<<map_grid(4), BN_THREADS, 0, s>>>(p);
+      eg_count_launch(EG_FAM_BN, 2);
+      bn_fwd_stats_kernel<T><<<red_grid(), BN_THREADS, 0, s>>>(p);
+      bn_fwd_apply_kernel<T><<<map_grid(BN_APPLY_UNROLL(T)), BN_THREADS, 0, s>>>(p);
     }
   } else if (which == 1) {
-    bn_fwd_apply_kernel<<<map_grid(4), BN_THREADS, 0, s>>>(p);
+    eg_count_launch(EG_FAM_BN, 1);
+    bn_fwd_apply_kernel<T><<<map_grid(BN_APPLY_UNROLL(T)), BN_THREADS, 0, s>>>(p);
   } else if (which == 2) {
     const long long rs_b = ceil_div(passes, BN_BWD_PASSES);
     if (p.fused_ok && rs_b * slices <= max_ctas) {
-      bn_bwd_fused_kernel<<<dim3((unsigned)slices, (unsigned)rs_b), BN_THREADS, 0, s>>>(p);
+      eg_count_launch(EG_FAM_BN, 1);
+      bn_bwd_fused_kernel<T><<<dim3((unsigned)slices, (unsigned)rs_b), BN_THREADS, 0, s>>>(p);
     } else {
-      bn_bwd_reduce_kernel<<<red_grid(), BN_THREADS, 0, s>>>(p);
-      bn_bwd_dx_kernel<<<map_grid(2), BN_THREADS, 0, s>>>(p);
+      eg_count_launch(EG_FAM_BN, 2);
+      bn_bwd_reduce_kernel<T><<<red_grid(), BN_THREADS, 0, s>>>(p);
+      bn_bwd_dx_kernel<T><<<map_grid(BN_DX_UNROLL(T)), BN_THREADS, 0, s>>>(p);
     }
   } else {
     return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s) {
+  return p.fp32 ? launch_bn_t<float>(p, which, sm_count, s) : launch_bn_t<__nv_bfloat16>(p, which, sm_count, s);
 }
 
 }  // namespace egb

@@ -37,6 +37,59 @@ __device__ __forceinline__ uint4 pack_bf16x8(const V8& r) {
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& u) { *reinterpret_cast<uint4*>(p) = u; }
 
+// Element-type abstraction: Raw8<T> = 8 consecutive channels of one row as they sit in memory
+// (bf16: one 16-byte word; fp32: two 16-byte words -- the reference's precision, event.cpp:279).
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+
+__device__ __forceinline__ Raw8<__nv_bfloat16> ld8(const __nv_bfloat16* p) {
+  Raw8<__nv_bfloat16> r; r.u = *reinterpret_cast<const uint4*>(p); return r;
+}
+__device__ __forceinline__ Raw8<float> ld8(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const Raw8<__nv_bfloat16>& r) { *reinterpret_cast<uint4*>(p) = r.u; }
+__device__ __forceinline__ void st8(float* p, const Raw8<float>& r) {
+  *reinterpret_cast<float4*>(p) = r.a;
+  *reinterpret_cast<float4*>(p + 4) = r.b;
+}
+__device__ __forceinline__ void zero8(Raw8<__nv_bfloat16>& r) { r.u = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void zero8(Raw8<float>& r) { r.a = r.b = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ V8 unpack8(const Raw8<__nv_bfloat16>& r) { return unpack_bf16x8(r.u); }
+__device__ __forceinline__ V8 unpack8(const Raw8<float>& r) {
+  V8 o;
+  o.v[0] = r.a.x; o.v[1] = r.a.y; o.v[2] = r.a.z; o.v[3] = r.a.w;
+  o.v[4] = r.b.x; o.v[5] = r.b.y; o.v[6] = r.b.z; o.v[7] = r.b.w;
+  return o;
+}
+__device__ __forceinline__ void pack8(const V8& v, Raw8<__nv_bfloat16>& r) { r.u = pack_bf16x8(v); }
+__device__ __forceinline__ void pack8(const V8& v, Raw8<float>& r) {
+  r.a = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  r.b = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+// d[e] = 0 where y[e] <= 0 (ReLU mask folded into the incoming gradient, done on the raw words)
+__device__ __forceinline__ void mask_le0(Raw8<__nv_bfloat16>& d, const Raw8<__nv_bfloat16>& y) {
+  const unsigned short* ys = reinterpret_cast<const unsigned short*>(&y.u);
+  unsigned short* ds = reinterpret_cast<unsigned short*>(&d.u);
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if ((ys[e] & 0x8000u) || (ys[e] & 0x7fffu) == 0u) ds[e] = 0;   // bf16 sign / zero test
+}
+__device__ __forceinline__ void mask_le0(Raw8<float>& d, const Raw8<float>& y) {
+  if (!(y.a.x > 0.f)) d.a.x = 0.f;
+  if (!(y.a.y > 0.f)) d.a.y = 0.f;
+  if (!(y.a.z > 0.f)) d.a.z = 0.f;
+  if (!(y.a.w > 0.f)) d.a.w = 0.f;
+  if (!(y.b.x > 0.f)) d.b.x = 0.f;
+  if (!(y.b.y > 0.f)) d.b.y = 0.f;
+  if (!(y.b.z > 0.f)) d.b.z = 0.f;
+  if (!(y.b.w > 0.f)) d.b.w = 0.f;
+}
+
 // -------------------------------------------------------------------------------------------
 // Reduce the per-thread 2x8 accumulators over the 32 row lanes, write this CTA's partial row
 // [128] = {sum a[64] | sum b[64]} for its slice.

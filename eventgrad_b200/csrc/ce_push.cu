@@ -1,4 +1,4 @@
-// eventgrad_b200 -- EXPERIMENTAL copy-engine push for the split step of dense gossip (decent).  sm_100a.
+// eventgrad_b200 -- copy-engine push for the split step of dense gossip (decent).  sm_100a.
 //
 // The split step (csrc/gossip.cu, phase 1 / phase 2) hides the neighbour pushes behind forward/backward,
 // but its phase-1 kernel occupies up to 128 CTAs for the ~0.2 ms the 2 x 70 MB take over NVLink -- SMs and
@@ -38,12 +38,13 @@ __global__ void ce_publish_pushed_kernel(const GossipParams p) {
 }
 
 cudaError_t launch_ce_push(const GossipParams& p, cudaStream_t s) {
-  if (p.push_l == nullptr || p.push_r == nullptr || p.fsm.enabled) return cudaErrorInvalidValue;
+  if (p.push_l == nullptr || p.fsm.enabled) return cudaErrorInvalidValue;   // push_r null: 2-rank ring, one copy
   const size_t nbytes = (size_t)p.tab.n_tiles * EG_TILE * sizeof(float);
+  eg_count_launch(EG_FAM_GOSSIP, 2);
   ce_wait_acks_kernel<<<1, 32, 0, s>>>(p);
   cudaError_t e = cudaMemcpyAsync(p.push_l, p.theta, nbytes, cudaMemcpyDeviceToDevice, s);
   if (e != cudaSuccess) return e;
-  if (p.push_r != p.push_l) {
+  if (p.push_r != nullptr && p.push_r != p.push_l) {
     e = cudaMemcpyAsync(p.push_r, p.theta, nbytes, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return e;
   }

@@ -174,12 +174,13 @@ __device__ __forceinline__ void cta_finish_tensors(const GossipParams& p, const 
 
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void push_tile(const GossipParams& p, size_t base, const F8& th) {
+  // push_r == nullptr: 2-rank ring, the one neighbour is both left and right and reads the single copy twice
   if (p.vec256_push) {
     st_f8(p.push_l + base, th);
-    st_f8(p.push_r + base, th);
+    if (p.push_r != nullptr) st_f8(p.push_r + base, th);
   } else {
     st_f8_v4(p.push_l + base, th);
-    st_f8_v4(p.push_r + base, th);
+    if (p.push_r != nullptr) st_f8_v4(p.push_r + base, th);
   }
 }
 #ifdef EG_DBUF
@@ -354,11 +355,14 @@ __device__ __forceinline__ void push_phase(const GossipParams& p, int step) {
   __shared__ int s_last;
   const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
   if (p.sync) {
+    __shared__ int s_ok;
     if (tid == 0) {   // WAR guard: neighbours have consumed what I pushed at step-1
-      wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
-      wait_ge(p.ack_from_r, (uint32_t)(step - 1), p.status, p.timeout_ns);
+      bool ok = wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
+      ok = wait_ge(p.ack_from_r, (uint32_t)(step - 1), p.status, p.timeout_ns) && ok;
+      s_ok = ok ? 1 : 0;
     }
     __syncthreads();
+    if (!s_ok) return;   // a wedged / dead peer (sticky status set): never overwrite memory it may still be reading
   }
   __shared__ TileInfo s_ti[EG_TI_CACHE];
   fill_tile_cache(p, s_ti);
@@ -390,6 +394,10 @@ __global__ void __launch_bounds__(EG_THREADS, 4) EG_SYM(gossip_step_kernel)(cons
   const int step = *p.fsm.pass_num + 1;
   const int n_tiles = p.tab.n_tiles;
   const bool push = p.do_push != 0 && p.phase != 2;
+  // Sticky failure: once any peer wait has timed out (this or an earlier launch) the step is a no-op on every
+  // CTA -- nothing is stored into a peer that may be wedged or dead, theta stops changing, and the host raises
+  // when it reads the status word.  (Uniform per CTA; the run is over, so a partial step does not matter.)
+  if (p.do_push && *reinterpret_cast<volatile int*>(p.status) != EG_OK) return;
 
 #ifdef EG_DBUF
   if (p.phase != 0 || !(p.sync && push)) return;   // the launcher rejects these; never reached
@@ -403,11 +411,14 @@ __global__ void __launch_bounds__(EG_THREADS, 4) EG_SYM(gossip_step_kernel)(cons
   fill_tile_cache(p, s_ti);
   if (p.phase == 2 && p.sync && p.do_push) {
     // split step, second half: the neighbours' pushes of this step were issued during my backward
+    __shared__ int s_pushed;
     if (tid == 0) {
-      wait_ge(p.pushed_from_l, (uint32_t)step, p.status, p.timeout_ns);
-      wait_ge(p.pushed_from_r, (uint32_t)step, p.status, p.timeout_ns);
+      bool ok = wait_ge(p.pushed_from_l, (uint32_t)step, p.status, p.timeout_ns);
+      ok = wait_ge(p.pushed_from_r, (uint32_t)step, p.status, p.timeout_ns) && ok;
+      s_pushed = ok ? 1 : 0;
     }
     __syncthreads();
+    if (!s_pushed) return;      // neighbour never pushed this step: do not average a stale inbox into theta
   }
 
   if (!(p.sync && push)) {
@@ -436,6 +447,9 @@ __global__ void __launch_bounds__(EG_THREADS, 4) EG_SYM(gossip_step_kernel)(cons
       s_ok = ok;
     }
     __syncthreads();
+    // ack timed out (or an earlier kernel already set the sticky status): the peer may still be reading what was
+    // pushed last step -- store nothing, mix nothing; the host raises on the status word
+    if (!s_ok) return;
 #endif
     const int D = p.group_iters;                   // pipeline depth in tiles
     const int iters = (n_tiles + G - 1) / G;
@@ -524,6 +538,7 @@ int gossip_max_grid(int device) {
 }
 
 cudaError_t launch_gossip_step(const GossipParams& p, int grid, cudaStream_t s) {
+  eg_count_launch(EG_FAM_GOSSIP, 1);
   if (p.mu != 0.f && p.mom != nullptr)
     gossip_step_kernel<true><<<grid, EG_THREADS, 0, s>>>(p);
   else
@@ -532,11 +547,13 @@ cudaError_t launch_gossip_step(const GossipParams& p, int grid, cudaStream_t s) 
 }
 
 cudaError_t launch_gossip_init(const GossipParams& p, int grid, int run_fsm, cudaStream_t s) {
+  eg_count_launch(EG_FAM_GOSSIP, 1);
   gossip_init_kernel<<<grid, EG_THREADS, 0, s>>>(p, run_fsm);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fsm_decide(const FsmDev& f, const TableDev& t, const float* ext_norm, cudaStream_t s) {
+  eg_count_launch(EG_FAM_GOSSIP, 1);
   fsm_decide_kernel<<<1, EG_THREADS, 0, s>>>(f, t, ext_norm);
   return cudaGetLastError();
 }
@@ -555,6 +572,7 @@ int gossip_dbuf_max_grid(int device) {
 // Dense iter-sync exchange only (decent): every tensor fires every step, inboxes hold 2 slots.
 cudaError_t launch_gossip_step_dbuf(const GossipParams& p, int grid, cudaStream_t s) {
   if (p.phase != 0 || !p.sync || !p.do_push || !p.do_mix || p.fsm.enabled) return cudaErrorInvalidValue;
+  eg_count_launch(EG_FAM_GOSSIP, 1);
   if (p.mu != 0.f && p.mom != nullptr)
     gossip_step_kernel_dbuf<true><<<grid, EG_THREADS, 0, s>>>(p);
   else

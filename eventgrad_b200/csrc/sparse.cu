@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_apply_kernel(const Spars
 // ------------------------------------------------------------------------------------------
 cudaError_t launch_sparse_select_push(const SparseParams& p, int grid, cudaStream_t s) {
   const int sz = p.tab.n_tensors;
+  eg_count_launch(EG_FAM_SPARSE, 9);
   sparse_hist_kernel<0><<<grid, EG_THREADS, 0, s>>>(p);
   sparse_scan_kernel<0><<<sz, EG_THREADS, 0, s>>>(p);
   sparse_hist_kernel<1><<<grid, EG_THREADS, 0, s>>>(p);
@@ -402,6 +403,7 @@ cudaError_t launch_sparse_select_push(const SparseParams& p, int grid, cudaStrea
 }
 
 cudaError_t launch_sparse_apply(const SparseParams& p, int grid, cudaStream_t s) {
+  eg_count_launch(EG_FAM_SPARSE, 1);
   sparse_apply_kernel<<<grid, EG_THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }

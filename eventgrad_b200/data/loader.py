@@ -28,6 +28,7 @@ class BatchLoader:
         self.gen = torch.Generator(device=self.device).manual_seed(seed * 7919 + sampler.rank)
         c, h, w = source.sample_shape
         self._stage = []
+        self._slot_ev = [None, None]      # event of the last H2D copy that READ each pinned slot
         if self.cuda:
             for _ in range(2):
                 xi = torch.empty(batch, c, h, w, dtype=torch.uint8).pin_memory()
@@ -69,6 +70,10 @@ class BatchLoader:
         if not self.cuda:
             return self.src.images[idx], self.src.labels[idx]
         xi, yi = self._stage[slot]
+        # the async H2D copy that last read this pinned slot must have EXECUTED before the host overwrites it: a
+        # stream-side wait_event is not enough, the host runs ahead of the GPU (no syncs in the step, CUDA graphs)
+        if self._slot_ev[slot] is not None:
+            self._slot_ev[slot].synchronize()
         n = idx.numel()
         torch.index_select(self.src.images, 0, idx, out=xi[:n])
         torch.index_select(self.src.labels, 0, idx, out=yi[:n])
@@ -104,6 +109,7 @@ class BatchLoader:
                 yd = yh.to(self.device, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
+            self._slot_ev[slot] = ev
             return xd, yd, ev
 
         if nb:
@@ -115,8 +121,7 @@ class BatchLoader:
             yd.record_stream(cur)
             x = self._decode(xd)
             if self.prefetch and b + 1 < nb:
-                # the pinned slot (b+1)&1 was last used by batch b-1 whose copy has completed
-                # (we waited on its event before decoding it)
+                # the pinned slot (b+1)&1 was last read by batch b-1's copy: _host_batch host-waits on its event
                 pending = issue(b + 1)
             yield x, yd
             if not self.prefetch and b + 1 < nb:

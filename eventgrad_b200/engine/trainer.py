@@ -38,13 +38,17 @@ def _compute_dtype(cfg: TrainConfig):
 class Trainer:
     def __init__(self, cfg: TrainConfig, env: DistEnv, group=None, train_source=None,
                  test_source=None):
-        self.cfg, self.env = cfg.validate(), env
+        cfg = cfg.validate().resolved(env.device.type, env.world)
+        self.cfg, self.env = cfg, env
         self.ring = Ring(env.rank, env.world)
         dev = env.device
         self.device = dev
-        if cfg.dtype == "tf32" and dev.type == "cuda":
-            torch.backends.cuda.matmul.allow_tf32 = True
-            torch.backends.cudnn.allow_tf32 = True
+        if dev.type == "cuda":
+            # fp32 means fp32: the reference computes in IEEE fp32 on the CPU (event.cpp:279), so TF32 is only used
+            # when asked for (cuDNN's allow_tf32 defaults to True in PyTorch)
+            tf32 = cfg.dtype == "tf32"
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
         if dev.type == "cuda":
             torch.backends.cudnn.benchmark = bool(cfg.cudnn_benchmark)
             if cfg.host_threads > 0:
@@ -95,13 +99,18 @@ class Trainer:
         self.epoch = 0
         self.steps_done = 0
         self._graphs = {}
+        self._graph_launches = {}                 # graph key -> kernels of OUR extension captured in that graph
+        self.own_launches_per_step = {}           # family -> kernels of our extension in the most recent step
+        self.own_launches_total = 0               # ... summed over every step executed so far (replays included)
         self._graph_warm = {}
         self._side = None
         self._graph_keepalive = []
         self.train_time_s = 0.0
         if cfg.resume:
-            sd = load_checkpoint(cfg.resume, arena=self.arena, backend=self.backend, model=self.model)
+            sd = load_checkpoint(cfg.resume, arena=self.arena, backend=self.backend, model=self.model,
+                                 loader=self.loader)
             self.epoch = int(sd["epoch"])
+            self.steps_done = int(sd.get("steps_done", 0))
         if env.rank == 0 and not cfg.quiet:
             t = self.arena.table
             print(f"Number of parameters - {t.n_tensors}", flush=True)       # event.cpp:127-130
@@ -131,6 +140,13 @@ class Trainer:
         return loss.detach()
 
     GRAPH_WARMUP_STEPS = 3
+
+    def _own_counts(self):
+        """Per-family count of kernels enqueued so far by OUR extension (csrc/api.h eg_count_launch)."""
+        if self.device.type != "cuda":
+            return None
+        from ..ops import ext
+        return dict(ext().launch_counts())
 
     def _fwd_bwd_launch(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """forward/backward + the backend's kernels, with the theta_k-only half of a split step
@@ -184,17 +200,21 @@ class Trainer:
             sx, sy = x.clone(), y.clone()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
+            before = self._own_counts()
             with torch.cuda.graph(g):
                 if whole:
                     sloss = self._fwd_bwd_launch(sx, sy)
                 else:
                     sloss = self._fwd_bwd(sx, sy)
+            after = self._own_counts()
+            self._graph_launches[key] = {k: after[k] - before.get(k, 0) for k in after}
             ent = (g, sx, sy, sloss)
             self._graphs[key] = ent
         g, sx, sy, sloss = ent
         sx.copy_(x)
         sy.copy_(y)
         g.replay()
+        self._replayed = self._graph_launches[key]
         if whole:
             self.backend.account_step()
         else:
@@ -205,10 +225,19 @@ class Trainer:
         """zero_grad -> forward -> loss -> backward -> [comm + average + SGD]."""
         if not getattr(self.backend, "zeroes_grad", False):
             self.arena.zero_grad()
+        before = self._own_counts()
+        self._replayed = None
         if self.cfg.cuda_graph and self.device.type == "cuda":
             loss = self._graphed_step(x, y)
         else:
             loss = self._eager_step(x, y)
+        if before is not None:
+            after = self._own_counts()
+            step = {k: after[k] - before.get(k, 0) for k in after}      # launched eagerly by this call ...
+            for k, v in (self._replayed or {}).items():                 # ... plus what the replayed graph holds
+                step[k] = step.get(k, 0) + v
+            self.own_launches_per_step = step
+            self.own_launches_total += sum(step.values())
         self.steps_done += 1
         self.last_loss = loss
         return loss
@@ -249,7 +278,9 @@ class Trainer:
                     self.logw.write_value(self.epoch, float(ep_losses[-1][1]))
             if cfg.ckpt_dir and cfg.ckpt_every and self.epoch % cfg.ckpt_every == 0:
                 save_checkpoint(ckpt_path(cfg.ckpt_dir, env.rank), epoch=self.epoch, arena=self.arena,
-                                backend=self.backend, model=self.model)
+                                backend=self.backend, model=self.model, loader=self.loader,
+                                steps_done=self.steps_done)
+                barrier(env)       # a slow writer must not leave its neighbours spinning against the device timeout
         self.backend.synchronize()
         self.train_time_s = time.perf_counter() - t0
         if env.rank == 0 and not cfg.quiet:
@@ -282,6 +313,9 @@ class Trainer:
         res["events_rank"] = self.backend.num_events()
         res["bytes_sent_rank"] = self.backend.bytes_sent()
         if cfg.algo != "cent":
+            # ranks may be skewed here (async mode has no per-step handshake; a slow checkpoint write or autotune on
+            # one rank): meet on the host first so nobody spins in the all-reduce kernel against its device timeout
+            barrier(env)
             self.backend.final_average()
         res["events_total"] = self.backend.total_events() if gossip else 0
         if gossip and env.rank == 0 and not cfg.quiet:

@@ -1,12 +1,12 @@
-"""Fused BatchNorm2d (+ residual add) (+ ReLU) for channels-last bf16 activations.
+"""Fused BatchNorm2d (+ residual add) (+ ReLU) for channels-last fp32 / bf16 activations.
 
 Front-end of csrc/bn_act.cu.  `FusedBNAct` is a drop-in nn.BatchNorm2d subclass (same parameter
 and buffer names, so the arena layout and state_dicts are unchanged) whose forward takes an
 optional residual and a relu flag; the ResNet blocks of the reference
 (/root/reference/dcifar10/common/resnet.hpp:39-52, :91-107) map onto it as
     bn(conv(x), relu=True)   and   bn(conv(x), residual=skip, relu=True).
-The CUDA path is taken for bf16 NHWC inputs on a GPU; anything else (CPU, fp32, NCHW) runs the
-equivalent PyTorch ops -- which are also the numerics oracle in tests/test_gpu_bn.py.
+The CUDA path is taken for fp32 (the reference's precision) or bf16 NHWC inputs on a GPU; anything else
+(CPU, NCHW, channel counts that are not a multiple of 64) runs the equivalent PyTorch ops -- which are also the numerics oracle in tests/test_gpu_bn.py.
 """
 from __future__ import annotations
 
@@ -35,13 +35,7 @@ def _workspace(device):
               "status": ctl[256:].data_ptr(), "C": C,
               # single-launch (spin-flag) variant for small tensors: measured SLOWER than the two-launch
               # split path inside a CUDA graph (1.52 vs 1.42 ms/step at batch 32), so it is opt-in
-              "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0,
-              # EXPERIMENTAL csrc/bn_act_v2.cu (ReLU bit mask instead of re-reading y in the backward);
-              # opt-in until it has been validated on hardware (tests/test_gpu_experimental.py)
-              "v2": os.environ.get("EGB_BN_V2", "0") == "1",
-              # EXPERIMENTAL csrc/bn_act_cluster.cu on top of v2: one launch per direction (thread-block
-              # cluster + DSMEM) for tensors whose 64-channel slice fits one cluster's shared memory
-              "cluster": 1 if os.environ.get("EGB_BN_CLUSTER", "0") == "1" else 0, "cluster_taken": 0}
+              "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0}
         _WS[device] = ws
     return ws
 
@@ -49,14 +43,14 @@ def _workspace(device):
 def _eligible(x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
     if os.environ.get("EGB_FUSED_BN", "1") == "0":
         return False
-    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+    if not (x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.dim() == 4):
         return False
     C = x.shape[1]
     if C % 64 or C > 2048:
         return False
     if not x.is_contiguous(memory_format=torch.channels_last):
         return False
-    if residual is not None and not (residual.dtype == torch.bfloat16 and residual.shape == x.shape
+    if residual is not None and not (residual.dtype == x.dtype and residual.shape == x.shape
                                      and residual.is_contiguous(memory_format=torch.channels_last)):
         return False
     return True
@@ -81,25 +75,12 @@ class _FusedBNActFn(torch.autograd.Function):
             invstd = torch.rsqrt(running_var + eps)
             rm = rv = nb = 0
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        ctx.v2 = bool(ws["v2"] and training)
-        if ctx.v2:
-            mask = torch.empty(M * C // 8 if relu else 0, dtype=torch.uint8, device=x.device)
-            with torch.cuda.device(x.device):
-                ws["cluster_taken"] += C_ext.bn_forward_v2(
-                    x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
-                    mask.data_ptr() if relu else 0, weight.data_ptr(), bias.data_ptr(),
-                    mean.data_ptr(), invstd.data_ptr(), rm, rv, nb, ws["partial"].data_ptr(),
-                    ws["f"][0], ws["status"], M, C, float(eps), float(momentum),
-                    1 if relu else 0, ws["sm"], ws["cluster"], stream)
-            ctx.save_for_backward(x, mask, weight, mean, invstd)
-            ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
-            return y
         with torch.cuda.device(x.device):
             C_ext.bn_forward(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
                              weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm, rv, nb,
                              ws["partial"].data_ptr(), ws["f"][0], ws["f"][1], ws["f"][2], ws["status"], M, C,
                              float(eps), float(momentum), 1 if relu else 0, 1 if training else 0, ws["fused"],
-                             ws["sm"], stream)
+                             ws["sm"], 1 if x.dtype == torch.float32 else 0, stream)
         ctx.save_for_backward(x, y, weight, mean, invstd)
         ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
         return y
@@ -113,28 +94,19 @@ class _FusedBNActFn(torch.autograd.Function):
         C_ext = ws["C"]
         N, C, H, W = x.shape
         M = N * H * W
-        if dy.dtype != torch.bfloat16 or not dy.is_contiguous(memory_format=torch.channels_last):
-            dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        if dy.dtype != x.dtype or not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        if ctx.v2:                                    # `y` is the bit mask here
-            with torch.cuda.device(x.device):
-                ws["cluster_taken"] += C_ext.bn_backward_v2(
-                    x.data_ptr(), y.data_ptr() if ctx.relu else 0, dy.data_ptr(), dx.data_ptr(),
-                    dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
-                    invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                    ws["partial"].data_ptr(), ws["b"][0], ws["status"], M, C,
-                    1 if ctx.relu else 0, ws["sm"], ws["cluster"], stream)
-            return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
         with torch.cuda.device(x.device):
             C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                               dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
                               invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws["partial"].data_ptr(),
                               ws["b"][0], ws["b"][1], ws["b"][2], ws["status"], M, C, 1 if ctx.relu else 0,
-                              ws["fused"], ws["sm"], stream)
+                              ws["fused"], ws["sm"], 1 if x.dtype == torch.float32 else 0, stream)
         return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
 
 

@@ -1,4 +1,4 @@
-"""tcgen05 fused Linear + bias (+ ReLU): front-end of csrc/linear_tc.cu.
+"""tcgen05 fused Linear + bias (+ ReLU): front-end of csrc/linear_tc_tma.cu (TMA, SWIZZLE_128B, persistent CTAs).
 
 Forward runs on the 5th-generation tensor cores (tcgen05.mma, accumulator in TMEM, bias/ReLU fused
 into the TMEM->register epilogue).  Backward uses plain library GEMMs (cuBLAS through torch): it is
@@ -35,14 +35,9 @@ def linear_tc_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
     y = torch.empty(M, N, dtype=out_dtype, device=x.device)
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        if os.environ.get("EGB_TC_LINEAR") == "tma":
-            # experimental TMA / SWIZZLE_128B / persistent variant (csrc/linear_tc_tma.cu): opt-in only
-            sm = torch.cuda.get_device_properties(x.device).multi_processor_count
-            ext().linear_tc_tma(xb.data_ptr(), wb.data_ptr(), 0 if bf is None else bf.data_ptr(), y.data_ptr(), M, N, K,
-                                1 if relu else 0, 1 if out_dtype == torch.bfloat16 else 0, sm, stream)
-        else:
-            ext().linear_tc(xb.data_ptr(), wb.data_ptr(), 0 if bf is None else bf.data_ptr(), y.data_ptr(), M, N, K,
-                            1 if relu else 0, 1 if out_dtype == torch.bfloat16 else 0, stream)
+        sm = torch.cuda.get_device_properties(x.device).multi_processor_count
+        ext().linear_tc(xb.data_ptr(), wb.data_ptr(), 0 if bf is None else bf.data_ptr(), y.data_ptr(), M, N, K,
+                        1 if relu else 0, 1 if out_dtype == torch.bfloat16 else 0, sm, stream)
     return y
 
 

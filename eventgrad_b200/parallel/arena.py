@@ -187,11 +187,18 @@ class ParamArena:
     def state_dict(self) -> dict:
         return {"theta": self.theta.detach().cpu().clone(),
                 "mom": None if self.mom is None else self.mom.detach().cpu().clone(),
-                "n_padded": self.table.n_padded, "numels": list(self.table.numels)}
+                "n_padded": self.table.n_padded, "numels": list(self.table.numels),
+                # theta is stored in PHYSICAL layout: conv weights are [O,kh,kw,I] under channels_last
+                "channels_last": bool(self.channels_last), "tile": int(TILE)}
 
     def load_state_dict(self, sd: dict) -> None:
         if list(sd["numels"]) != list(self.table.numels):
             raise ValueError("checkpoint tensor table does not match this model")
+        if "channels_last" in sd and (bool(sd["channels_last"]) != bool(self.channels_last)
+                                      or int(sd.get("tile", TILE)) != int(TILE)):
+            raise ValueError(f"checkpoint was written with channels_last={sd['channels_last']} tile={sd.get('tile')}: "
+                             f"the arena stores conv weights in physical layout, resume with the same setting "
+                             f"(this run: channels_last={self.channels_last} tile={TILE})")
         self.theta.copy_(sd["theta"].to(self.theta.device))
         if self.mom is not None and sd.get("mom") is not None:
             self.mom.copy_(sd["mom"].to(self.mom.device))

@@ -21,7 +21,14 @@ from .base import CommBackend, StepLog
 from .window import DistBootstrap, Layout, SymmWindow, Window, wants_symm_window
 
 ONE_SHOT_MAX_BYTES = 512 * 1024        # above this the all-reduce switches to two-shot
-DEFAULT_TIMEOUT_NS = 30_000_000_000    # a wedged peer trips the sticky status instead of hanging
+
+
+def default_timeout_ns(cfg=None) -> int:
+    """Bound of every device-side peer wait (a wedged / dead peer trips the sticky status word instead of hanging
+    the GPU): TrainConfig.peer_timeout_s, overridable with EGB_PEER_TIMEOUT_S."""
+    import os
+    sec = float(os.environ.get("EGB_PEER_TIMEOUT_S", getattr(cfg, "peer_timeout_s", 30.0) or 30.0))
+    return int(sec * 1e9)
 
 
 def _table_of(model) -> TensorTable:
@@ -29,8 +36,10 @@ def _table_of(model) -> TensorTable:
 
 
 def _wants_dbuf(cfg) -> bool:
-    """csrc/gossip_dbuf.cu applies to the dense, iter-sync, single-kernel decent step only."""
-    return (bool(getattr(cfg, "double_buffer", False)) and cfg.algo == "decent" and cfg.sync_mode == "iter"
+    """csrc/gossip_dbuf.cu (two inbox slots, no WAR ack) applies to the dense, iter-sync, single-kernel decent step
+    only; there it is the default (double_buffer=None), `--no-double-buffer` selects the single-slot + ack protocol."""
+    db = getattr(cfg, "double_buffer", None)
+    return ((db is None or bool(db)) and cfg.algo == "decent" and cfg.sync_mode == "iter"
             and not getattr(cfg, "overlap_push", False))
 
 
@@ -40,7 +49,7 @@ def build_layout(table: TensorTable, cfg, world: int, max_grid: int) -> Layout:
     lay.add("theta", n)
     lay.add("grad", n)
     if cfg.algo in ("decent", "event"):
-        slots = 2 if _wants_dbuf(cfg) else 1      # experimental double-buffered decent: slot = step & 1
+        slots = 2 if _wants_dbuf(cfg) else 1      # double-buffered decent: slot = step & 1
         lay.add("inbox_l", n * slots)
         lay.add("inbox_r", n * slots)
     if cfg.algo == "spevent":
@@ -72,7 +81,7 @@ def preallocate_arena_buffers(model, cfg, env, group=None, bootstrap=None):
     if _wants_dbuf(cfg):
         max_grid = min(max_grid, C.gossip_dbuf_max_grid(env.device.index or 0))
     lay = build_layout(table, cfg, env.world, max_grid)
-    symm = wants_symm_window(env) and bootstrap is None      # EXPERIMENTAL NVLS path (EGB_NVLS=1)
+    symm = wants_symm_window(env) and bootstrap is None      # NVLS path: torch symmetric memory + multicast mapping
     win = (SymmWindow if symm else Window)(lay, env.rank, env.world, env.device)
     theta = win.view("theta", torch.float32)
     grad = win.view("grad", torch.float32)
@@ -85,7 +94,7 @@ class P2PBackend(CommBackend):
 
     def __init__(self, cfg, arena: ParamArena, ring, env, group=None, symm=None,
                  grid_cap: int = 0, defer_connect: bool = False, group_iters: int = 2,
-                 timeout_ns: int = DEFAULT_TIMEOUT_NS, vec256_push: bool = True, push_grid: int = 0):
+                 timeout_ns: int = 0, vec256_push: bool = True, push_grid: int = 0):
         super().__init__(cfg, arena, ring)
         from ..ops import ext
         self.C = ext()
@@ -104,7 +113,7 @@ class P2PBackend(CommBackend):
         # balance: every CTA gets the same number of tiles (+-1 only on the last round)
         rounds = -(-t.n_tiles // self.grid)
         self.grid = -(-t.n_tiles // rounds)
-        self.group_iters, self.timeout_ns, self.vec256_push = group_iters, timeout_ns, vec256_push
+        self.group_iters, self.timeout_ns, self.vec256_push = group_iters, timeout_ns or default_timeout_ns(cfg), vec256_push
         self.sync = cfg.sync_mode == "iter"
         self.gossip = cfg.algo in ("decent", "event", "spevent")
         self.sparse = cfg.algo == "spevent"
@@ -115,6 +124,7 @@ class P2PBackend(CommBackend):
         self.dbuf = _wants_dbuf(cfg) and self.do_comm
         self.ce_push = bool(getattr(cfg, "ce_push", False)) and self.overlap and cfg.algo == "decent" and self.sync
         self.nvls = self.nvls_step = False      # set in connect() when the window has a multicast mapping
+        self.wire_dedup = False
         self.push_grid = push_grid
         self.recv_rms = cfg.dataset == "mnist"
         dev = self.dev
@@ -243,6 +253,12 @@ class P2PBackend(CommBackend):
             if dense:
                 gp.update({"inbox_l": win.addr("inbox_l"), "inbox_r": win.addr("inbox_r"),
                            "push_l": win.addr("inbox_r", L), "push_r": win.addr("inbox_l", R)})
+                # 2-rank ring: left == right.  Push theta ONCE (into the peer's inbox_r) and let the peer read that
+                # copy as both L and R: (theta + 2 theta')/3 is unchanged bit for bit, the link carries 69.8 MB per
+                # step instead of 139.6 MB.  Event/byte counters keep the reference's logical count (2 messages).
+                self.wire_dedup = self.ring.world == 2 and L == R
+                if self.wire_dedup:
+                    gp.update({"inbox_l": win.addr("inbox_r"), "push_r": 0})
             elif self.sparse:
                 gp.update({"inbox_l": P(self.rep_l), "inbox_r": P(self.rep_r)})
             self.gp = gp
@@ -484,6 +500,8 @@ class P2PBackend(CommBackend):
         if self.sparse:
             for k in ("prev", "rep_l", "rep_r"):
                 getattr(self, k).copy_(sd[k].to(self.dev))
+        if self.log_ring is not None:
+            self._drained = self.pass_num          # log rows of the steps before the checkpoint are not replayed
         # NOTE: handshake counters (flags / acks) restart from pass_num on every rank
         if self.gossip:
             self._init_norms(run_fsm=False)

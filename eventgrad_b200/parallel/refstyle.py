@@ -121,3 +121,18 @@ class ReferenceStyleBackend(CollectiveBackend):
                 g.div_(self.ring.world)
             self.bytes += t.n_elems * 4
         self._opt()
+
+    # host-resident FSM state travels with the checkpoint too (plain floats: weights_only-safe)
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["h_fsm"] = {"thres": [float(v) for v in self.h_thres], "last_norm": [float(v) for v in self.h_last_norm],
+                       "last_iter": [float(v) for v in self.h_last_iter],
+                       "slopes": [[float(v) for v in row] for row in self.h_slopes]}
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        h = sd.get("h_fsm")
+        if h is not None:
+            self.h_thres, self.h_last_norm = list(h["thres"]), list(h["last_norm"])
+            self.h_last_iter, self.h_slopes = list(h["last_iter"]), [list(r) for r in h["slopes"]]

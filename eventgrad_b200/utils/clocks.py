@@ -12,6 +12,81 @@ _Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
 
+class NvmlClockSampler:
+    """In-process NVML poller (nvidia_ml_py): ~2 ms period, so even a 40 ms timed region carries >= 5 samples (the
+    nvidia-smi -lms poller of round 1 returned 0 samples at N >= 2).  Only samples taken between mark_begin() and
+    stop() count; the handle is looked up by the CUDA device's UUID, so CUDA_VISIBLE_DEVICES remapping is harmless."""
+
+    _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, cuda_index: int = 0, period_ms: float = 2.0):
+        self.idx, self.period = cuda_index, period_ms / 1e3
+        self.samples = []
+        self._stop = threading.Event()
+        self._begin = None
+        self._t = None
+        self.h = None
+        self.nv = None
+
+    def start(self) -> "NvmlClockSampler":
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+            return self
+        nv, h = self.nv, self.h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
+        def pump():
+            import time
+            while not self._stop.is_set():
+                try:
+                    self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                         nv.nvmlDeviceGetPowerUsage(h) / 1e3, int(reasons_fn(h))))
+                except Exception:
+                    pass
+                time.sleep(self.period)
+        self._t = threading.Thread(target=pump, daemon=True)
+        self._t.start()
+        return self
+
+    def mark_begin(self) -> None:
+        import time
+        self._begin = time.perf_counter()
+
+    def stop(self) -> Dict:
+        import time
+        end = time.perf_counter()
+        self._stop.set()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self._t.join(timeout=1)
+        t0 = self._begin or 0.0
+        inside = [s for s in self.samples if t0 <= s[0] <= end]
+        try:
+            mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        reasons = set()
+        for s in inside:
+            for bit, nm in self._BITS.items():
+                if s[3] & bit:
+                    reasons.add(nm)
+        sm = [float(s[1]) for s in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "power_w_max": max((s[2] for s in inside), default=None),
+                "samples": len(sm), "period_ms": self.period * 1e3, "source": "nvml", "reasons": sorted(reasons)}
+
+
 class ClockSampler:
     def __init__(self, gpu_index: int = 0, period_ms: int = 100):
         self.gpu, self.period = gpu_index, period_ms

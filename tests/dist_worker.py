@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--warm", type=int, default=4)
     ap.add_argument("--sync-mode", default="iter")
     ap.add_argument("--overlap", action="store_true")
-    ap.add_argument("--double-buffer", action="store_true")
+    ap.add_argument("--double-buffer", action=argparse.BooleanOptionalAction, default=None)
     ap.add_argument("--fresh-replicas", action="store_true")
     ap.add_argument("--ce-push", action="store_true")
     a = ap.parse_args()

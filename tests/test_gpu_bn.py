@@ -120,3 +120,110 @@ def test_single_launch_variant_matches_split(monkeypatch):
     # both variants round their results to bf16; fp32 statistics may differ in the last bit
     for a, b in zip(outs[0], outs[1]):
         torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fp32 activations (the reference's precision, /root/reference/dcifar10/event/event.cpp:259-276): same kernels
+# instantiated for float, compared against plain PyTorch fp32 at fp32 tolerances
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (7, 128, 16, 16), (5, 256, 8, 8), (3, 512, 4, 4), (1, 64, 3, 5),
+                                   (256, 64, 32, 32), (64, 128, 16, 16)])   # last two: split path
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False), (False, True)])
+@pytest.mark.parametrize("fused_small", [0, 1])
+def test_fused_bn_act_fp32(shape, relu, res, fused_small):
+    import eventgrad_b200.ops.bn_act as B
+    N, C, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mk = lambda s, b: (torch.randn(N, C, H, W, generator=g, device="cuda") * s + b).contiguous(memory_format=torch.channels_last)
+    x, r, dy = mk(1.5, 0.3), mk(1.0, 0.0), mk(1.0, 0.0)
+    B._workspace(x.device)["fused"] = fused_small
+    try:
+        bn = FusedBNAct(C).cuda().train()
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.5, 0.5)
+        ref = torch.nn.BatchNorm2d(C).cuda().train()
+        ref.load_state_dict(bn.state_dict())
+        xa = x.clone().requires_grad_(True)
+        ra = r.clone().requires_grad_(True) if res else None
+        assert _eligible(xa, ra)
+        y = bn(xa, residual=ra, relu=relu)
+        assert y.dtype == torch.float32 and y.is_contiguous(memory_format=torch.channels_last)
+        y.backward(dy)
+        xb = x.clone().requires_grad_(True)
+        rb = r.clone().requires_grad_(True) if res else None
+        yb = ref(xb)
+        if res:
+            yb = yb + rb
+        if relu:
+            yb = torch.relu(yb)
+        yb.backward(dy)
+    finally:
+        B._workspace(x.device)["fused"] = 0
+    torch.testing.assert_close(y, yb, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(bn.running_mean, ref.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn.running_var, ref.running_var, rtol=1e-5, atol=1e-6)
+    # elements exactly on the ReLU boundary may flip between two correct fp32 evaluations; everything else is tight
+    scale = float(xb.grad.abs().max()) + 1e-6
+    bad = ((xa.grad - xb.grad).abs() / scale > 1e-4).float().mean()
+    assert float(bad) < 2e-5, float(bad)
+    # dgamma / dbeta are fp32 statistics accumulated in double by the kernel: tight check
+    gs = float(ref.weight.grad.abs().max()) + 1e-6
+    assert float((bn.weight.grad - ref.weight.grad).abs().max()) / gs < 2e-4
+    bs = float(ref.bias.grad.abs().max()) + 1e-6
+    assert float((bn.bias.grad - ref.bias.grad).abs().max()) / bs < 2e-4
+    if res:
+        rs = float(rb.grad.abs().max()) + 1e-6
+        assert float(((ra.grad - rb.grad).abs() / rs > 1e-5).float().mean()) < 2e-5
+    assert B.bn_status(x.device) == 0
+
+
+def test_fp32_training_tracks_plain_pytorch_50_steps():
+    """Default product path on a GPU (fp32, NHWC, fused fp32 BN kernels, whole-step CUDA graph, fused SGD step kernel)
+    against a plain PyTorch fp32 NCHW model + torch.optim.SGD from the same seed and batches: the loss trajectories
+    stay within 1e-3 over 50 steps (VERDICT r1 'done' criterion for the fp32 headline)."""
+    import torch.nn.functional as F
+    from eventgrad_b200.config import preset
+    from eventgrad_b200.data import synthetic_source
+    from eventgrad_b200.engine.trainer import Trainer
+    from eventgrad_b200.models import build_model
+    from eventgrad_b200.utils.dist import DistEnv
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    cfg = preset("cifar_event", algo="decent", backend="p2p", device="cuda", dtype="fp32", train_samples=512,
+                 test_samples=64, batch_size=32, epochs=100, quiet=True, augment=False, sampler="sequential",
+                 cudnn_benchmark=False)
+    tr = Trainer(cfg, DistEnv(0, 1, 0, dev, "none"), train_source=synthetic_source("cifar10", 512).pin())
+    assert tr.cfg.channels_last and tr.cfg.cuda_graph          # the fast path IS the default on a GPU
+    torch.manual_seed(cfg.seed)
+    ref = build_model("resnet18").to(dev).train()
+    with torch.no_grad():      # same initial weights as the arena
+        for (n, p), q in zip(ref.named_parameters(), tr.model.parameters()):
+            p.copy_(q.detach())
+    opt = torch.optim.SGD(ref.parameters(), lr=cfg.lr, momentum=cfg.momentum)
+    import os
+    l_ours, l_ref = [], []
+    it = iter(tr.loader)
+    for s in range(50):
+        try:
+            x, y = next(it)
+        except StopIteration:
+            it = iter(tr.loader)
+            x, y = next(it)
+        xr = x.detach().clone().contiguous()       # plain NCHW copy for the reference model
+        l_ours.append(tr.train_step(x, y).clone())
+        os.environ["EGB_FUSED_BN"] = "0"
+        try:
+            opt.zero_grad(set_to_none=True)
+            lr_ = F.cross_entropy(ref(xr), y)
+            lr_.backward()
+            opt.step()
+        finally:
+            os.environ["EGB_FUSED_BN"] = "1"
+        l_ref.append(lr_.detach())
+    tr.backend.check_status()
+    a, b = torch.stack(l_ours).cpu(), torch.stack(l_ref).cpu()
+    assert torch.isfinite(a).all()
+    assert float((a - b).abs().max()) < 1e-3, (a - b).abs().max()
+    tr.close()

@@ -48,12 +48,16 @@ def _mask_pad(w, g):
 
 @pytest.mark.parametrize("R", [1, 2, 3, 4])
 @pytest.mark.parametrize("mu", [0.0, 0.9])
-def test_decent_bitwise_vs_simulator(R, mu):
-    cfg = _cfg("decent", momentum=mu)
+@pytest.mark.parametrize("dbuf", [None, False])       # None = default: double-buffered inboxes, no WAR ack
+def test_decent_bitwise_vs_simulator(R, mu, dbuf):
+    cfg = _cfg("decent", momentum=mu, double_buffer=dbuf)
     w = _world(cfg, R)
+    assert all(be.dbuf == (dbuf is None) for be in w.backends)
+    if R == 2:
+        assert all(be.wire_dedup for be in w.backends)     # 2-rank ring: theta crosses the link once
     t = w.arenas[0].table
     sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "decent", lr=cfg.lr, momentum=mu, serial_skip=False)
-    for s in range(5):
+    for s in range(7):      # odd and even inbox slots both used several times
         g = _mask_pad(w, _grads(R, t.n_padded, 100 + s))
         w.step(g)
         sim.step([x.cpu() for x in g])
@@ -284,4 +288,59 @@ def test_split_step_overlap_mode_matches_simulator(algo, R):
         assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r}"
         if algo != "decent":
             assert be.num_events() == sim.events[r]
+    w.close()
+
+
+@pytest.mark.parametrize("R", [1, 2, 3])
+def test_ce_push_split_step_matches_simulator(R):
+    """csrc/ce_push.cu: ack wait kernel -> cudaMemcpyAsync (x1 on a 2-rank ring, else x2) -> pushed-flag kernel as the
+    push half of the split step (decent), R virtual ranks on one GPU, bit-exact vs the oracle."""
+    cfg = _cfg("decent", overlap_push=True, ce_push=True)
+    w = _world(cfg, R)
+    assert all(be.ce_push for be in w.backends)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "decent", lr=cfg.lr, momentum=cfg.momentum, serial_skip=False)
+    for s in range(8):
+        g = _mask_pad(w, _grads(R, t.n_padded, 700 + s))
+        w.step(g)
+        sim.step([x.cpu() for x in g])
+    torch.cuda.synchronize()
+    for r, be in enumerate(w.backends):
+        be.check_status()
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"rank {r}"
+    w.close()
+
+
+@pytest.mark.parametrize("mode", ["fused_ack", "fused_dbuf", "split"])
+def test_dead_peer_trips_timeout_and_stops_pushing(mode):
+    """Failure detection on the PRODUCT backend: virtual rank 1 stops stepping; rank 0's next step must come back
+    within the device timeout with the sticky status EG_ERR_TIMEOUT (no hang), and from then on rank 0 must not
+    store into the dead peer's inbox any more (honour s_ok)."""
+    import time
+    from eventgrad_b200.ops.local_world import LocalWorld
+    kw = {"fused_ack": dict(double_buffer=False), "fused_dbuf": dict(), "split": dict(overlap_push=True)}[mode]
+    cfg = _cfg("decent", **kw)
+    w = LocalWorld(cfg, 2, lambda: build_model("cnn2"), grid_cap=6, timeout_ns=300_000_000)     # 0.3 s
+    t = w.arenas[0].table
+    for s in range(3):
+        w.step(_mask_pad(w, _grads(2, t.n_padded, 900 + s)))
+    torch.cuda.synchronize()
+    for be in w.backends:
+        be.check_status()
+    peer_inbox = w.backends[1].win.view("inbox_r", torch.float32)
+    t0 = time.perf_counter()
+    with torch.cuda.stream(w.streams[0]):          # only rank 0 steps: its neighbour is "dead"
+        w.backends[0].step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert dt < 5.0, f"step against a dead peer took {dt:.1f} s (timeout is 0.3 s per wait)"
+    with pytest.raises(RuntimeError, match="status 1"):
+        w.backends[0].check_status()
+    snap = peer_inbox.clone()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(w.streams[0]):          # status is sticky: waits return at once, nothing is stored
+        w.backends[0].step()
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 2.0
+    assert torch.equal(peer_inbox, snap), "rank 0 kept writing into the dead peer's inbox after the timeout"
     w.close()

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 128), (1000, 784, 128), (300, 128, 256), (77, 16, 16), (4096, 784, 64),
-                                   (129, 200, 32)])
+                                   (129, 200, 32), (60000, 784, 128)])
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("out", [torch.bfloat16, torch.float32])
 def test_linear_tc_forward(M, K, N, relu, out):

@@ -90,3 +90,46 @@ def test_p2p_checkpoint_roundtrip(tmp_path):
         t = tr.arena.table
         assert torch.equal(tr.arena.flat(tr.arena.theta, 0).to(torch.bfloat16), tr.arena.shadow[:t.numels[0]])
     tr.close()
+
+
+def test_native_loader_on_cuda_path():
+    """--native-loader on: C++ prefetch thread (csrc/host_loader.h) feeding pinned slots + async H2D gives the same
+    batches as the Python staging path."""
+    from eventgrad_b200.data import BatchLoader, ShardSampler
+    src = synthetic_source("cifar10", 1000).pin()
+    a = BatchLoader(src, ShardSampler(1000, 1, 0, "sequential"), 64, "cuda", native="on")
+    b = BatchLoader(src, ShardSampler(1000, 1, 0, "sequential"), 64, "cuda", native="off")
+    assert a.native is not None
+    for (xa, ya), (xb, yb) in zip(a, b):
+        assert torch.equal(xa, xb) and torch.equal(ya, yb)
+
+
+def test_p2p_file_write_logs(tmp_path):
+    """Reference debug files (send<r>/recv<r>.txt, event.cpp:203-227) from the DEVICE log ring of the p2p backend
+    (MNIST self-loop, 1 GPU): one row per step, 3 fields per tensor on the send side."""
+    cfg = preset("mnist_event", backend="p2p", device="cuda", train_samples=640, test_samples=128, epochs=1,
+                 quiet=True, file_write=1, log_dir=str(tmp_path))
+    tr = Trainer(cfg, _env(), train_source=synthetic_source("mnist", 640).pin(),
+                 test_source=synthetic_source("mnist", 128, train=False).pin())
+    tr.fit()
+    tr.finalize()
+    send = open(tmp_path / "send0.txt").read().splitlines()
+    recv = open(tmp_path / "recv0.txt").read().splitlines()
+    assert len(send) == 10 and len(recv) == 10 and len(send[0].split(",  ")) == 8 * 3 + 1
+    assert len(open(tmp_path / "train0.txt").read().splitlines()) == 10
+    tr.close()
+
+
+def test_gpu_defaults_are_the_fast_path_and_fp32_uses_fused_bn():
+    """No execution flags: on a GPU the Trainer runs NHWC + whole-step CUDA graph, and the fp32 activations go through
+    the fused BN kernels (csrc/bn_act.cu instantiated for float) -- counted through the extension's launch counter."""
+    from eventgrad_b200.ops import ext
+    C = ext()
+    n0 = C.launch_count()
+    tr, _ = _run(steps=6)                               # dtype defaults to fp32
+    assert tr.cfg.dtype == "fp32" and tr.cfg.channels_last and tr.cfg.cuda_graph
+    assert len(tr._graphs) == 1
+    per_step = tr.own_launches_per_step
+    assert per_step.get("bn", 0) >= 4 * 13 and per_step.get("gossip", 0) >= 1, per_step
+    assert C.launch_count() > n0
+    tr.close()

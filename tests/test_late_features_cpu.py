@@ -1,5 +1,4 @@
-"""CPU checks of the host-side logic behind the late round-1 additions (their kernels need a GPU:
-tests/test_gpu_experimental.py)."""
+"""CPU checks of the host-side logic around the p2p backend options (their kernels are exercised by the gpu tier)."""
 import pytest
 import torch
 
@@ -10,12 +9,32 @@ from eventgrad_b200.parallel.arena import TensorTable
 from eventgrad_b200.parallel.p2p import _wants_dbuf, build_layout
 
 
-def test_cli_flags_of_experimental_paths_parse():
+def test_cli_flags_of_backend_options_parse():
     cfg = parse_cli("decent", ["0", "--double-buffer", "--ce-push", "--overlap-push"])
     assert cfg.double_buffer and cfg.ce_push and cfg.overlap_push
     cfg = parse_cli("cifar_spevent", ["0", "1", "1.0", "10", "--fresh-replicas"])
     assert cfg.spevent_fresh_replicas and cfg.topk_percent == 10.0
-    assert not parse_cli("decent", ["0"]).double_buffer
+    assert parse_cli("decent", ["0"]).double_buffer is None                 # auto
+    assert parse_cli("decent", ["0", "--no-double-buffer"]).double_buffer is False
+    cfg = parse_cli("cifar_event", ["0", "1", "1.0", "--no-cuda-graph", "--no-channels-last", "--peer-timeout-s", "5"])
+    assert cfg.cuda_graph is False and cfg.channels_last is False and cfg.peer_timeout_s == 5.0
+
+
+def test_execution_switches_resolve_to_the_fast_path_on_cuda_only():
+    """device=cuda implies NHWC + fused BN, whole-step CUDA graph and (N>=2, decent/event) overlapped pushes unless
+    turned off; on the CPU everything stays off (bench config == CLI default config)."""
+    c = parse_cli("cifar_event", ["0", "1", "1.0"])
+    assert c.channels_last is None and c.cuda_graph is None and c.overlap_push is None
+    g8 = c.resolved("cuda", 8)
+    assert g8.channels_last and g8.cuda_graph and g8.overlap_push
+    g1 = c.resolved("cuda", 1)
+    assert g1.channels_last and g1.cuda_graph and not g1.overlap_push
+    cpu = c.resolved("cpu", 2)
+    assert not cpu.channels_last and not cpu.cuda_graph and not cpu.overlap_push
+    off = parse_cli("cifar_event", ["0", "1", "1.0", "--no-overlap-push", "--no-cuda-graph"]).resolved("cuda", 8)
+    assert off.overlap_push is False and off.cuda_graph is False and off.channels_last
+    assert not parse_cli("cifar_spevent", ["0", "1", "1.0", "10"]).resolved("cuda", 8).overlap_push
+    assert not parse_cli("cent", []).resolved("cuda", 8).overlap_push
 
 
 def test_double_buffer_applies_to_dense_iter_sync_fused_decent_only():
@@ -26,7 +45,8 @@ def test_double_buffer_applies_to_dense_iter_sync_fused_decent_only():
         TrainConfig(algo="decent", sync_mode="async", **base).validate()
     assert not _wants_dbuf(TrainConfig(algo="decent", overlap_push=True, **base).validate())
     t = TensorTable.from_named(list(build_model("cnn2").named_parameters()), 2048)
-    one = build_layout(t, TrainConfig(algo="decent", dataset="mnist", model="cnn2").validate(), 4, 64)
+    assert _wants_dbuf(TrainConfig(algo="decent", dataset="mnist", model="cnn2").validate())     # default: on
+    one = build_layout(t, TrainConfig(algo="decent", dataset="mnist", model="cnn2", double_buffer=False).validate(), 4, 64)
     two = build_layout(t, TrainConfig(algo="decent", **base).validate(), 4, 64)
     assert two.nbytes("inbox_l") == 2 * one.nbytes("inbox_l") == 2 * t.n_padded * 4
     assert two.offset("inbox_r") % 256 == 0 and two.size > one.size
@@ -65,22 +85,3 @@ def test_set_sparse_init_guards():
     sp.pass_num = 1
     with pytest.raises(RuntimeError):
         sp.set_sparse_init(z, z, z)
-
-
-def test_bn_cluster_plan_covers_every_row_and_fits_shared_memory():
-    """Host-side plan of csrc/bn_act_cluster.cu (pure host code in the extension, runs without a GPU)."""
-    from eventgrad_b200.ops import ext
-    C = ext()
-    for which, slabs, cap in ((0, 1, 1536), (2, 2, 768)):
-        for M in list(range(1, 600, 7)) + [1024, 2048, 4095, 4096, 8192, 12288, 12289, 16384, 24576, 24577, 32768, 262144]:
-            cs, rows, smem = C.bn_cluster_plan(M, which)
-            if cs == 0:
-                assert M > 16 * cap - 16 * 31, (M, which)        # only genuinely too-large slices are refused
-                continue
-            assert cs in (1, 2, 4, 8, 16)
-            assert rows % 32 == 0 and rows <= cap
-            assert cs * rows >= M                                   # every row has an owner
-            assert (cs - 1) * rows < M + rows                       # no more than one (partially) idle tail CTA chain
-            assert smem == rows * 128 * slabs <= 196608
-    assert C.bn_cluster_plan(2048, 0)[0] == 8                       # batch-32 stage 3: one slice over 8 SMs
-    assert C.bn_cluster_plan(8192, 2)[0] == 16                      # batch-32 stage 2 backward needs the 16-CTA cluster
