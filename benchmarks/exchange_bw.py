@@ -65,30 +65,21 @@ def main():
     base = dict(dataset="mnist", model=a.model, lr=1e-2, momentum=0.9)   # mnist => comm even at W=1 (self loop)
 
     # ---- dense fused gossip (decent) -----------------------------------------------------------
-    for name, kw in (("v256", dict(vec256_push=True)), ("v128", dict(vec256_push=False)),
-                     ("d1", dict(group_iters=1)), ("d4", dict(group_iters=4))):
-        cfg = TrainConfig(algo="decent", sync_mode="iter", **base).validate()
+    # "ack_*": single inbox slot + WAR ack (round-1 protocol); "dbuf": two slots, no ack (the default since round 2)
+    for name, dbuf, kw in (("ack_v256", False, dict(vec256_push=True)), ("ack_v128", False, dict(vec256_push=False)),
+                           ("ack_d1", False, dict(group_iters=1)), ("ack_d4", False, dict(group_iters=4)),
+                           ("dbuf", None, dict()), ("dbuf_d4", None, dict(group_iters=4))):
+        cfg = TrainConfig(algo="decent", sync_mode="iter", double_buffer=dbuf, **base).validate()
         arena, be = make(cfg, env, a.model, **kw)
+        assert be.dbuf == (dbuf is None)
         n_bytes = arena.table.n_elems * 4
         ms = timed(be.step, env, a.iters)
         be.check_status()
-        res[f"gossip_dense_{name}"] = {"ms": ms, "egress_GBps_per_gpu": 2 * n_bytes / ms / 1e6,
-                                      "frac_of_770": 2 * n_bytes / ms / 1e6 / 770,
+        wire = (1 if be.wire_dedup else 2) * n_bytes          # 2-rank ring: theta crosses the link once
+        res[f"gossip_dense_{name}"] = {"ms": ms, "egress_GBps_per_gpu": wire / ms / 1e6,
+                                      "frac_of_770": wire / ms / 1e6 / 770, "frac_of_900": wire / ms / 1e6 / 900,
+                                      "wire_bytes_per_gpu": wire,
                                       "hbm_GBps": 9 * arena.table.n_padded * 4 / ms / 1e6, "grid": be.grid}
-        be.close()
-        del arena, be
-        torch.cuda.empty_cache()
-
-    # ---- experimental: double-buffered dense gossip (no WAR ack), opt-in --------------------------
-    if os.environ.get("EGB_EXPERIMENTAL") == "1":
-        cfg = TrainConfig(algo="decent", sync_mode="iter", double_buffer=True, **base).validate()
-        arena, be = make(cfg, env, a.model)
-        assert be.dbuf
-        n_bytes = arena.table.n_elems * 4
-        ms = timed(be.step, env, a.iters)
-        be.check_status()
-        res["gossip_dense_dbuf"] = {"ms": ms, "egress_GBps_per_gpu": 2 * n_bytes / ms / 1e6,
-                                    "frac_of_770": 2 * n_bytes / ms / 1e6 / 770, "grid": be.grid}
         be.close()
         del arena, be
         torch.cuda.empty_cache()
@@ -103,7 +94,7 @@ def main():
             be.C.gossip_step_phase(be.gp, 2, be.grid, be._stream())
         ms_both = timed(both, env, a.iters)
         res[f"push_only_grid{g}"] = {"ms_push_plus_mix": ms_both}
-    if os.environ.get("EGB_EXPERIMENTAL") == "1":
+    if True:
         def both_ce():                                   # copy engines instead of the SM push kernel
             be.C.ce_push(be.gp, be._stream())
             be.C.gossip_step_phase(be.gp, 2, be.grid, be._stream())
@@ -160,8 +151,24 @@ def main():
                 th.add_(mom, alpha=-1e-2)
                 g.zero_()
             entry["ms_nccl_eager"] = timed(nccl_step, env, a.iters)
-        res[f"allreduce_sgd_{model}"] = entry
         be.close(); del arena, be; torch.cuda.empty_cache()
+        if W > 1 and model != "mlp":
+            # NVLS: window in torch symmetric memory, in-switch reduction (multimem.ld_reduce) + multicast store
+            os.environ["EGB_NVLS"] = "1"
+            try:
+                arena, be = make(cfg, env, model)
+                if be.nvls_step:
+                    entry["ms_fused_nvls"] = timed(be.step, env, a.iters)
+                    be.check_status()
+                    entry["busbw_GBps_nvls"] = (2 * (W - 1) / W) * n_bytes / entry["ms_fused_nvls"] / 1e6
+                else:
+                    entry["ms_fused_nvls"] = None
+                be.close(); del arena, be; torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                entry["nvls_error"] = repr(e)[:200]
+            finally:
+                os.environ["EGB_NVLS"] = "0"
+        res[f"allreduce_sgd_{model}"] = entry
 
     # ---- NCCL-only gossip baseline -------------------------------------------------------------
     if W > 1 and not a.skip_nccl:

@@ -72,7 +72,7 @@ class TrainConfig:
     # ---- execution ---------------------------------------------------------
     device: str = "auto"             # auto | cuda | cpu
     dtype: str = "fp32"              # fp32 | tf32 | bf16 (compute dtype; arena is fp32)
-    channels_last: Optional[bool] = None   # None = auto: NHWC activations/weights + fused BN kernels on CUDA
+    channels_last: Optional[bool] = None   # None = auto on CUDA: NHWC for bf16/tf32, NCHW for fp32 (fused BN kernels in both)
     cuda_graph: Optional[bool] = None      # None = auto: whole-step CUDA graph on CUDA
     max_steps: int = 0               # >0: stop after this many steps (tests / bench)
     cudnn_benchmark: bool = True     # cuDNN autotune: best steady state, but every new conv shape costs a
@@ -113,7 +113,10 @@ class TrainConfig:
         p2p = self.backend == "p2p" or (self.backend == "auto" and cuda)
         kw = {}
         if self.channels_last is None:
-            kw["channels_last"] = cuda
+            # bf16 / tf32: NHWC (tensor-core convolutions want it).  fp32: cuDNN's IEEE-fp32 convolutions are NCHW
+            # kernels -- fed NHWC they transpose around every conv (measured 36.9 vs 27.8 ms/step on B200), so the
+            # reference-precision path stays NCHW; the fused BN kernels exist for both layouts
+            kw["channels_last"] = cuda and self.dtype != "fp32"
         if self.cuda_graph is None:
             kw["cuda_graph"] = cuda
         if self.overlap_push is None:

@@ -49,6 +49,7 @@ struct FsmDev {
   int enabled;         // 0: decent / cent (no trigger: fire[] stays all-ones)
 };
 
+struct SparseParams;
 // ------------------------------------------------------------------ fused gossip step
 // One launch = push theta_k to both ring neighbours (only tensors whose trigger fired) ->
 // [iter-sync: flag handshake] -> (theta+L+R)/3 -> SGD(+momentum) -> write theta_{k+1} (+bf16
@@ -97,6 +98,8 @@ struct GossipParams {
   int zero_grad;
   int group_iters;          // iter-sync software-pipeline depth in tiles (push j, mix j-D)
   int vec256_push;          // 1: 256-bit peer stores, 0: 2x128-bit
+  const struct SparseParams* sparse;   // spevent: device copy of the sparse parameters -> the kernel's prologue scatters
+                            // the arrived (value, index) records into inbox_l / inbox_r (the replicas) first
   int need_norm;            // 0: skip norm-on-write + trigger entirely (decent/cent without logs)
   int phase;                // 0 fused step | 1 push only (side stream, overlaps backward) | 2 wait+mix+SGD
 };
@@ -170,12 +173,15 @@ struct SparseParams {
   const int* t_k;           // [sz] k_i
   const int* t_rec_off;     // [sz] record offset (words)
   // scratch
-  unsigned int* hist;       // [sz][2048]
-  unsigned int* sel_prefix; // [sz] radix prefix of the k-th largest |diff| found so far
-  unsigned int* sel_remain; // [sz] rank still to resolve inside the prefix bucket
-  unsigned int* tile_gt;    // [n_tiles] elements > tau in the tile
-  unsigned int* tile_eq;    // [n_tiles] elements == tau
-  unsigned int* t_gt_total; // [sz]
+  unsigned int* hist;       // [sz][2048] (left all-zero by every launch)
+  unsigned int* sel_prefix; // [sz] pass 1: top 11 bits of tau; after pass 2: tau = the k-th largest |diff| key
+  unsigned int* sel_remain; // [sz] pass 1: rank inside the bucket; after pass 2: number of keys == tau to select
+  uint32_t* cand;           // [n_tiles * EG_TILE] candidate keys (low 21 bits), tensor i at t_tile_start[i]*EG_TILE
+  unsigned int* cand_cnt;   // [sz]
+  unsigned int* done1;      // [sz] per-tensor tile-completion counters of pass 1 / pass 2
+  unsigned int* done2;
+  unsigned long long* desc; // [n_tiles] look-back descriptors of pass 3
+  unsigned int* bar;        // [2] grid barrier of the receive prologue (arrivals, generation)
   const int* fire;
   const int* pass_num;
   unsigned int* ticket;
@@ -184,6 +190,8 @@ struct SparseParams {
   TableDev tab;
   int sync;
 };
+// 3 launches: histogram+pick, candidates+exact threshold, ordered compaction straight into the neighbours' inboxes.
+// `grid` must be a co-resident persistent grid (pass 3 uses a decoupled look-back between CTAs).
 cudaError_t launch_sparse_select_push(const SparseParams& p, int grid, cudaStream_t s);
 cudaError_t launch_sparse_apply(const SparseParams& p, int grid, cudaStream_t s);
 

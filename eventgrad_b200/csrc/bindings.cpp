@@ -49,7 +49,7 @@ static const std::unordered_map<std::string, Setter<GossipParams>> kGossip = {
     NUMF(GossipParams, timeout_ns), NUMF(GossipParams, lr), NUMF(GossipParams, mu),
     NUMF(GossipParams, do_mix), NUMF(GossipParams, do_push), NUMF(GossipParams, sync),
     NUMF(GossipParams, send_ack), NUMF(GossipParams, zero_grad), NUMF(GossipParams, group_iters),
-    NUMF(GossipParams, vec256_push), NUMF(GossipParams, need_norm), NUMF(GossipParams, phase), TAB_FIELDS(GossipParams),
+    NUMF(GossipParams, vec256_push), PTRF(GossipParams, sparse), NUMF(GossipParams, need_norm), NUMF(GossipParams, phase), TAB_FIELDS(GossipParams),
     PTRF2(GossipParams, fsm, thres), PTRF2(GossipParams, fsm, last_norm), PTRF2(GossipParams, fsm, last_iter),
     PTRF2(GossipParams, fsm, slopes), PTRF2(GossipParams, fsm, fire), PTRF2(GossipParams, fsm, cur_norm),
     PTRF2(GossipParams, fsm, counters), PTRF2(GossipParams, fsm, pass_num), PTRF2(GossipParams, fsm, log_ring),
@@ -77,8 +77,9 @@ static const std::unordered_map<std::string, Setter<SparseParams>> kSparse = {
     PTRF(SparseParams, done_to_l), PTRF(SparseParams, done_to_r), PTRF(SparseParams, ack_from_l),
     PTRF(SparseParams, ack_from_r), PTRF(SparseParams, ack_to_l), PTRF(SparseParams, ack_to_r),
     PTRF(SparseParams, t_k), PTRF(SparseParams, t_rec_off), PTRF(SparseParams, hist),
-    PTRF(SparseParams, sel_prefix), PTRF(SparseParams, sel_remain), PTRF(SparseParams, tile_gt),
-    PTRF(SparseParams, tile_eq), PTRF(SparseParams, t_gt_total), PTRF(SparseParams, fire),
+    PTRF(SparseParams, sel_prefix), PTRF(SparseParams, sel_remain), PTRF(SparseParams, cand),
+    PTRF(SparseParams, cand_cnt), PTRF(SparseParams, done1), PTRF(SparseParams, done2), PTRF(SparseParams, desc),
+    PTRF(SparseParams, bar), PTRF(SparseParams, fire),
     PTRF(SparseParams, pass_num), PTRF(SparseParams, ticket), PTRF(SparseParams, status),
     NUMF(SparseParams, timeout_ns), NUMF(SparseParams, sync), TAB_FIELDS(SparseParams),
 };
@@ -170,6 +171,12 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("sparse_select_push", [](const SparseParams& p, int grid, uintptr_t s) {
     check(launch_sparse_select_push(p, grid, S(s)), "sparse_select_push");
+  });
+  // device copy of a SparseParams block (GossipParams.sparse points at it: receive prologue of the mix kernel)
+  m.attr("SPARSE_PARAMS_BYTES") = (int)sizeof(SparseParams);
+  m.def("sparse_params_to_device", [](const SparseParams& p, uintptr_t dst) {
+    check(cudaMemcpy(reinterpret_cast<void*>(dst), &p, sizeof(SparseParams), cudaMemcpyHostToDevice),
+          "sparse_params_to_device");
   });
   m.def("sparse_apply", [](const SparseParams& p, int grid, uintptr_t s) {
     check(launch_sparse_apply(p, grid, S(s)), "sparse_apply");

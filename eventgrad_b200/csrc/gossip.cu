@@ -24,6 +24,7 @@
 // finishing step k+1 needs the receiver's flags of step k+1 (model-checked: tests/test_protocol_model.py).
 #include "api.h"
 #include "common.cuh"
+#include "sparse_apply.cuh"
 
 #ifdef EG_DBUF
 #define EG_SYM(name) name##_dbuf
@@ -409,6 +410,11 @@ __global__ void __launch_bounds__(EG_THREADS, 4) EG_SYM(gossip_step_kernel)(cons
 #endif
   __shared__ TileInfo s_ti[EG_TI_CACHE];
   fill_tile_cache(p, s_ti);
+#ifndef EG_DBUF
+  // spevent: receive side first -- scatter the records that arrived for this step into the replicas
+  // (inbox_l / inbox_r point at them), grid barrier, then the dense mix below reads them tile by tile
+  if (p.sparse != nullptr) sparse_apply_prologue(*p.sparse, p.sparse->bar);
+#endif
   if (p.phase == 2 && p.sync && p.do_push) {
     // split step, second half: the neighbours' pushes of this step were issued during my backward
     __shared__ int s_pushed;

@@ -5,25 +5,25 @@
 // sender then sets prev[idx] = value; the receiver scatters the record into a persistent
 // replica of that neighbour and mixes with the FULL replicas.
 //
-// Device design (all fired tensors of the model in one batched, segmented pass -- no per-tensor
-// launches, no host round trip, nothing sorted):
-//   1. exact k-th largest key per tensor by a 3-digit (11/11/10 bit) MSD radix select on the
-//      monotone uint32 image of |diff|; histograms are segmented by tensor (a tile belongs to
-//      exactly one tensor) and accumulated in shared memory;
-//   2. per-tile (> tau, == tau) counts + a per-tensor exclusive scan give every selected
-//      element a deterministic slot (ties at tau resolved towards the lowest index);
-//   3. compaction writes (value, int32 index) straight into BOTH neighbours' inbox records
-//      over NVLink and updates prev in the same pass;
-//   4. sparse_apply scatters the freshly arrived records into the replicas (skipping records
-//      that did not change), after which the dense mix+SGD kernel (gossip.cu) runs on
-//      (theta, rep_l, rep_r).
-#include "api.h"
-#include "common.cuh"
+// Device design, round 2: THREE launches, three streaming passes over (theta, prev), for ALL fired tensors of
+// the model at once (segmented by tensor: a tile belongs to exactly one tensor), nothing sorted, no host round
+// trip.  (Round 1 needed 9 launches / 5 passes and was as slow as the dense step it is meant to undercut.)
+//   1. sparse_hist_kernel   pass 1: shared-memory histogram of the top 11 bits of the monotone uint32 image of
+//                           |diff|, merged per tensor; the CTA that completes a tensor picks the bucket that
+//                           holds the k-th largest key (no separate scan launch).
+//   2. sparse_cand_kernel   pass 2: the low 21 bits of every key in that bucket go to a compact per-tensor
+//                           candidate list (one atomic per TILE, block-scan inside); the CTA that completes a
+//                           tensor resolves the remaining 21 bits (11 + 10) on that small list alone ->
+//                           exact threshold tau and the number of tau-ties to take.
+//   3. sparse_compact_kernel pass 3: single-pass ordered compaction with a decoupled look-back over the tiles of
+//                           each tensor (ties at tau resolved towards the lowest index => the selected SET is
+//                           deterministic), writing (value, int32 index) straight into BOTH neighbours' record
+//                           inboxes over NVLink and updating prev in the same pass.
+// The receive side (scatter of freshly arrived records into the replicas) is the PROLOGUE of the dense
+// mix+SGD kernel (gossip.cu, `sparse_apply_prologue` below + one grid barrier), so a spevent step is 4 launches.
+#include "sparse_apply.cuh"
 
 namespace egb {
-
-#define SP_BINS 2048
-#define SP_MAX_TENSORS 4096
 
 __device__ __forceinline__ uint32_t diff_key(float a, float b) {
   return __float_as_uint(fabsf(__fsub_rn(a, b)));   // non-negative floats order like uints
@@ -36,15 +36,93 @@ __device__ __forceinline__ int tile_valid(const TableDev& tab, int t, int i) {
   return rem < EG_TILE ? rem : EG_TILE;
 }
 
-// ---------------------------------------------------------------- 1. radix-select histograms
-// pass 0: digit = key[31:21]; pass 1: key[20:10] among keys matching prefix; pass 2: key[9:0].
-template <int PASS>
+// Walk a shared-memory histogram of `nb` buckets (nb <= 2048, 256 threads x 8 buckets) from the TOP bucket down
+// to the one holding the element of rank `remain` (1-based, counted from the largest).  Returns, to every thread,
+// {bucket, number of elements in higher buckets}.  `sh` is left untouched.
+__device__ __forceinline__ void block_pick(const unsigned int* sh, int nb, unsigned remain, unsigned* digit,
+                                           unsigned* above) {
+  __shared__ unsigned int wsum[EG_WARPS];
+  __shared__ unsigned int s_digit, s_above;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned int loc[8], tot = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {                 // descending order: position q <-> bucket nb-1-q
+    const int q = tid * 8 + e;
+    const unsigned c = (q < nb) ? sh[nb - 1 - q] : 0u;
+    loc[e] = c;
+    tot += c;
+  }
+  unsigned int inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();                               // previous use of wsum / s_digit is over
+  if (lane == 31) wsum[warp] = inc;
+  if (tid == 0) {
+    s_digit = 0u;
+    s_above = 0u;
+  }
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += wsum[w];
+  unsigned int excl = woff + inc - tot;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (remain > excl && remain <= excl + loc[e]) {       // exactly one (thread, e) satisfies this
+      s_digit = (unsigned)(nb - 1 - (tid * 8 + e));
+      s_above = excl;
+    }
+    excl += loc[e];
+  }
+  __syncthreads();
+  *digit = s_digit;
+  *above = s_above;
+}
+
+// "Which tensors did this CTA complete?"  Tiles [t0, t1) were processed by this CTA; add the number of tiles it
+// contributed to each tensor's completion counter; tensors whose counter reaches their tile count are returned
+// in s_own (their data from EVERY CTA is visible after the fences).  Tiles ascend => equal tensors consecutive.
+#define SP_MAX_OWN 64
+__device__ __forceinline__ int claim_completed(const TableDev& tab, unsigned int* done, int t0, int t1, int* s_own,
+                                               int* s_nown) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int nown = 0, cur = -1, cnt = 0;
+    for (int t = t0; t <= t1; ++t) {
+      const int i = (t < t1) ? tab.tile_tensor[t] : -2;
+      if (i != cur) {
+        if (cur >= 0) {
+          const unsigned prev = atomicAdd(done + cur, (unsigned)cnt);
+          if (prev + (unsigned)cnt == (unsigned)tab.t_tile_count[cur]) {
+            done[cur] = 0u;                                  // ready for the next step
+            if (nown < SP_MAX_OWN) s_own[nown++] = cur;
+          }
+        }
+        cur = i;
+        cnt = 0;
+      }
+      ++cnt;
+    }
+    *s_nown = nown;
+    __threadfence();
+  }
+  __syncthreads();
+  return *s_nown;
+}
+
+// ---------------------------------------------------------------- 1. histogram of the top 11 key bits
 __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const SparseParams p) {
   __shared__ unsigned int sh[SP_BINS];
+  __shared__ int s_own[SP_MAX_OWN];
+  __shared__ int s_nown;
   const int tid = threadIdx.x;
   const int G = gridDim.x;
-  const int per = (p.tab.n_tiles + G - 1) / G;          // blocked tile ranges: few tensor switches
-  const int t0 = blockIdx.x * per, t1 = min(p.tab.n_tiles, t0 + per);
+  int per = (p.tab.n_tiles + G - 1) / G;                // blocked tile ranges: few tensor switches per CTA
+  if (per > SP_MAX_OWN) per = SP_MAX_OWN;               // (host sizes the grid so that this never truncates)
+  const int t0 = min(p.tab.n_tiles, blockIdx.x * per), t1 = min(p.tab.n_tiles, t0 + per);
   int cur = -1;
   auto flush = [&](int tensor) {
     __syncthreads();
@@ -60,6 +138,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const Sparse
   flush(-1);
   for (int t = t0; t < t1; ++t) {
     const int i = p.tab.tile_tensor[t];
+    if (tid == 0) p.desc[t] = 0ull;                      // look-back descriptors of pass 3 start EMPTY
     if (!p.fire[i]) continue;
     if (i != cur) {
       flush(cur);
@@ -68,168 +147,167 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const Sparse
     const int valid = tile_valid(p.tab, t, i);
     const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
     const F8 a = ld_f8(p.theta + base), b = ld_f8(p.prev + base);
-    uint32_t prefix = 0;
-    if (PASS > 0) prefix = p.sel_prefix[i];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (tid * EG_VEC + e >= valid) continue;
-      const uint32_t key = diff_key(a.v[e], b.v[e]);
-      if (PASS == 0) {
-        atomicAdd(&sh[key >> 21], 1u);
-      } else if (PASS == 1) {
-        if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 0x7FFu], 1u);
-      } else {
-        if ((key >> 10) == prefix) atomicAdd(&sh[key & 0x3FFu], 1u);
-      }
+      atomicAdd(&sh[diff_key(a.v[e], b.v[e]) >> 21], 1u);
     }
   }
   flush(cur);
-}
-
-// One CTA per tensor: walk the histogram from the top bucket down to the one holding the
-// element of rank `remain` (1-based, counted from the largest); extend the prefix.
-template <int PASS>
-__global__ void __launch_bounds__(EG_THREADS) sparse_scan_kernel(const SparseParams p) {
-  const int i = blockIdx.x;
-  if (!p.fire[i]) return;
-  __shared__ unsigned int wsum[EG_WARPS];
-  __shared__ unsigned int s_digit, s_above;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned int* h = p.hist + (size_t)i * SP_BINS;
-  const int nb = (PASS == 2) ? 1024 : SP_BINS;
-  // descending order: position q <-> bucket nb-1-q ; thread owns 8 consecutive positions
-  unsigned int loc[8], tot = 0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int q = tid * 8 + e;
-    const unsigned c = (q < nb) ? h[nb - 1 - q] : 0u;
-    loc[e] = c;
-    tot += c;
-    if (q < nb) h[nb - 1 - q] = 0u;            // ready for the next pass / next step
-  }
-  // block exclusive scan of tot
-  unsigned int inc = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) wsum[warp] = inc;
-  __syncthreads();
-  unsigned int woff = 0;
-  for (int w = 0; w < warp; ++w) woff += wsum[w];
-  unsigned int excl = woff + inc - tot;
-  const unsigned int remain = (PASS == 0) ? (unsigned)p.t_k[i] : p.sel_remain[i];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    if (remain > excl && remain <= excl + loc[e]) {       // exactly one (thread, e) satisfies this
-      s_digit = (unsigned)(nb - 1 - (tid * 8 + e));
-      s_above = excl;
+  // ---- tensors completed by this CTA: pick the bucket of the k-th largest key, clear the histogram ----------
+  const int nown = claim_completed(p.tab, p.done1, t0, t1, s_own, &s_nown);
+  for (int o = 0; o < nown; ++o) {
+    const int i = s_own[o];
+    if (!p.fire[i]) continue;                            // uniform per CTA
+    unsigned int* h = p.hist + (size_t)i * SP_BINS;
+    __syncthreads();
+    for (int bkt = tid; bkt < SP_BINS; bkt += EG_THREADS) {
+      sh[bkt] = __ldcg(h + bkt);
+      h[bkt] = 0u;                                       // ready for the next step
     }
-    excl += loc[e];
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t prev = (PASS == 0) ? 0u : p.sel_prefix[i];
-    const int bits = (PASS == 2) ? 10 : 11;
-    p.sel_prefix[i] = (prev << bits) | s_digit;
-    p.sel_remain[i] = remain - s_above;                   // rank inside the chosen bucket
+    __syncthreads();
+    unsigned digit, above;
+    block_pick(sh, SP_BINS, (unsigned)p.t_k[i], &digit, &above);
+    if (tid == 0) {
+      p.sel_prefix[i] = digit;                           // top 11 bits of tau
+      p.sel_remain[i] = (unsigned)p.t_k[i] - above;      // rank inside that bucket
+      p.cand_cnt[i] = 0u;
+    }
   }
 }
 
-// ---------------------------------------------------------------- 2. per-tile counts + scan
-__global__ void __launch_bounds__(EG_THREADS, 4) sparse_count_kernel(const SparseParams p) {
-  __shared__ unsigned int wg[EG_WARPS], we[EG_WARPS];
+// ---------------------------------------------------------------- 2. candidates of the chosen bucket
+__global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const SparseParams p) {
+  __shared__ unsigned int sh[SP_BINS];
+  __shared__ unsigned int wsum[EG_WARPS];
+  __shared__ unsigned int s_base;
+  __shared__ int s_own[SP_MAX_OWN];
+  __shared__ int s_nown;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = blockIdx.x; t < p.tab.n_tiles; t += gridDim.x) {
+  const int G = gridDim.x;
+  int per = (p.tab.n_tiles + G - 1) / G;
+  if (per > SP_MAX_OWN) per = SP_MAX_OWN;
+  const int t0 = min(p.tab.n_tiles, blockIdx.x * per), t1 = min(p.tab.n_tiles, t0 + per);
+  for (int t = t0; t < t1; ++t) {
     const int i = p.tab.tile_tensor[t];
     if (!p.fire[i]) continue;
-    const uint32_t tau = p.sel_prefix[i];
+    const uint32_t prefix = p.sel_prefix[i];
     const int valid = tile_valid(p.tab, t, i);
     const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
     const F8 a = ld_f8(p.theta + base), b = ld_f8(p.prev + base);
-    unsigned g = 0, q = 0;
+    uint32_t keys[8];
+    unsigned m = 0, c = 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (tid * EG_VEC + e >= valid) continue;
-      const uint32_t key = diff_key(a.v[e], b.v[e]);
-      g += key > tau;
-      q += key == tau;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      g += __shfl_xor_sync(0xffffffffu, g, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane == 0) {
-      wg[warp] = g;
-      we[warp] = q;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned G2 = 0, Q2 = 0;
-      for (int w = 0; w < EG_WARPS; ++w) {
-        G2 += wg[w];
-        Q2 += we[w];
+      keys[e] = diff_key(a.v[e], b.v[e]);
+      if (tid * EG_VEC + e < valid && (keys[e] >> 21) == prefix) {
+        m |= 1u << e;
+        ++c;
       }
-      p.tile_gt[t] = G2;
-      p.tile_eq[t] = Q2;
     }
-    __syncthreads();
-  }
-}
-
-// one warp per tensor: exclusive prefix of (gt, eq) over the tensor's tiles, in place
-__global__ void __launch_bounds__(EG_THREADS) sparse_tilescan_kernel(const SparseParams p) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * EG_WARPS + (threadIdx.x >> 5);
-  if (i >= p.tab.n_tensors || !p.fire[i]) return;
-  const int ts = p.tab.t_tile_start[i], tc = p.tab.t_tile_count[i];
-  unsigned cg = 0, ce = 0;
-  for (int s = 0; s < tc; s += 32) {
-    const int t = ts + s + lane;
-    unsigned g = (s + lane < tc) ? p.tile_gt[t] : 0u, q = (s + lane < tc) ? p.tile_eq[t] : 0u;
-    unsigned gi = g, qi = q;
+    // block exclusive scan of c; ONE global atomic per tile reserves the tile's slice of the candidate list
+    unsigned inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned vg = __shfl_up_sync(0xffffffffu, gi, o), vq = __shfl_up_sync(0xffffffffu, qi, o);
-      if (lane >= o) {
-        gi += vg;
-        qi += vq;
-      }
+      const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
     }
-    if (s + lane < tc) {
-      p.tile_gt[t] = cg + gi - g;
-      p.tile_eq[t] = ce + qi - q;
+    __syncthreads();
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < EG_WARPS; ++w) {
+      if (w < warp) woff += wsum[w];
+      total += wsum[w];
     }
-    cg += __shfl_sync(0xffffffffu, gi, 31);
-    ce += __shfl_sync(0xffffffffu, qi, 31);
+    if (tid == 0) s_base = total ? atomicAdd(p.cand_cnt + i, total) : 0u;
+    __syncthreads();
+    if (c) {
+      uint32_t* dst = p.cand + (size_t)p.tab.t_tile_start[i] * EG_TILE + s_base + woff + inc - c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (m & (1u << e)) *dst++ = keys[e] & 0x1FFFFFu;
+    }
   }
-  if (lane == 0) p.t_gt_total[i] = cg;
+  // ---- tensors completed by this CTA: resolve the remaining 21 bits on the candidate list alone --------------
+  const int nown = claim_completed(p.tab, p.done2, t0, t1, s_own, &s_nown);
+  for (int o = 0; o < nown; ++o) {
+    const int i = s_own[o];
+    if (!p.fire[i]) continue;
+    const uint32_t* cand = p.cand + (size_t)p.tab.t_tile_start[i] * EG_TILE;
+    const unsigned n = __ldcg(p.cand_cnt + i);
+    unsigned remain = p.sel_remain[i];
+    // digit 2: bits [20:10]
+    __syncthreads();
+    for (int bkt = tid; bkt < SP_BINS; bkt += EG_THREADS) sh[bkt] = 0u;
+    __syncthreads();
+    for (unsigned j = tid; j < n; j += EG_THREADS) atomicAdd(&sh[__ldcg(cand + j) >> 10], 1u);
+    __syncthreads();
+    unsigned d2, above;
+    block_pick(sh, SP_BINS, remain, &d2, &above);
+    remain -= above;
+    // digit 3: bits [9:0] among the candidates that match digit 2
+    __syncthreads();
+    for (int bkt = tid; bkt < 1024; bkt += EG_THREADS) sh[bkt] = 0u;
+    __syncthreads();
+    for (unsigned j = tid; j < n; j += EG_THREADS) {
+      const uint32_t c = __ldcg(cand + j);
+      if ((c >> 10) == d2) atomicAdd(&sh[c & 0x3FFu], 1u);
+    }
+    __syncthreads();
+    unsigned d3;
+    block_pick(sh, 1024, remain, &d3, &above);
+    if (tid == 0) {
+      p.sel_prefix[i] = (p.sel_prefix[i] << 21) | (d2 << 10) | d3;    // tau: the k-th largest key, exactly
+      p.sel_remain[i] = remain - above;                               // how many keys == tau are selected (>= 1)
+    }
+  }
 }
 
-// ---------------------------------------------------------------- 3. compaction -> peers
+// ---------------------------------------------------------------- 3. ordered compaction -> peers
+// Look-back descriptor of a tile: [63:62] state (1 = aggregate of this tile, 2 = inclusive prefix over the tensor's
+// tiles up to and including this one), [61:31] count(key > tau), [30:0] count(key == tau).
+#define SP_AGG (1ull << 62)
+#define SP_INC (2ull << 62)
+__device__ __forceinline__ unsigned long long sp_pack(unsigned long long st, unsigned gt, unsigned eq) {
+  return st | ((unsigned long long)gt << 31) | (unsigned long long)eq;
+}
+__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const SparseParams p) {
   __shared__ unsigned int wg[EG_WARPS], we[EG_WARPS];
-  __shared__ int s_last;
+  __shared__ unsigned int s_pg, s_pe;                   // exclusive prefix of this tile inside its tensor
+  __shared__ int s_last, s_ok;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int step = *p.pass_num + 1;
   if (p.sync) {
     if (tid == 0) {   // WAR guard on the neighbours' record inboxes
-      wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
-      wait_ge(p.ack_from_r, (uint32_t)(step - 1), p.status, p.timeout_ns);
+      bool ok = wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
+      ok = wait_ge(p.ack_from_r, (uint32_t)(step - 1), p.status, p.timeout_ns) && ok;
+      s_ok = ok ? 1 : 0;
     }
     __syncthreads();
+    if (!s_ok) return;                                  // wedged peer: store nothing (status is sticky)
   }
+  // tiles in ASCENDING order, strided over the persistent grid: tile t-1 is processed by the neighbouring CTA in
+  // the same round, so the look-back never waits on work that has not been scheduled (all CTAs co-resident)
   for (int t = blockIdx.x; t < p.tab.n_tiles; t += gridDim.x) {
     const int i = p.tab.tile_tensor[t];
     if (!p.fire[i]) continue;
     const uint32_t tau = p.sel_prefix[i];
     const unsigned need_eq = p.sel_remain[i];
-    const unsigned gt_total = p.t_gt_total[i];
     const int k = p.t_k[i];
+    const int ts = p.tab.t_tile_start[i];
     const int valid = tile_valid(p.tab, t, i);
-    const int first = (t - p.tab.t_tile_start[i]) * EG_TILE;
+    const int first = (t - ts) * EG_TILE;
     const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
     const F8 a = ld_f8(p.theta + base);
     F8 b = ld_f8(p.prev + base);
@@ -255,12 +333,64 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
         qi += vq;
       }
     }
+    __syncthreads();                                    // previous tile's readers of wg / s_pg are done
     if (lane == 31) {
       wg[warp] = gi;
       we[warp] = qi;
     }
     __syncthreads();
-    unsigned og = p.tile_gt[t], oe = p.tile_eq[t];
+    if (warp == 0) {
+      // tile totals -> publish -> decoupled look-back over the preceding tiles of the SAME tensor (one warp,
+      // 32 descriptors per round) -> publish the inclusive prefix
+      unsigned G2 = 0, Q2 = 0;
+#pragma unroll
+      for (int w = 0; w < EG_WARPS; ++w) {
+        G2 += wg[w];
+        Q2 += we[w];
+      }
+      unsigned pg = 0, pe = 0;
+      if (t == ts) {
+        if (lane == 0) st_desc(p.desc + t, sp_pack(SP_INC, G2, Q2));
+      } else {
+        if (lane == 0) st_desc(p.desc + t, sp_pack(SP_AGG, G2, Q2));
+        int hi = t - 1;                                 // next descriptor to inspect (descending)
+        const uint64_t t_start = globaltimer_ns();
+        bool done = false;
+        while (!done) {
+          const int s = hi - lane;
+          unsigned long long d = SP_INC;                // lanes below the tensor's first tile: neutral terminator
+          if (s >= ts) {
+            do {
+              d = ld_desc(p.desc + s);
+              if ((d >> 62) == 0ull && globaltimer_ns() - t_start > p.timeout_ns) {   // never hang the GPU
+                atomicExch(p.status, EG_ERR_TIMEOUT);
+                d = SP_INC;
+              }
+            } while ((d >> 62) == 0ull);
+          }
+          const unsigned inc_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+          const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 32;     // first lane (= nearest tile) holding a prefix
+          unsigned cg = (lane <= stop && s >= ts) ? (unsigned)((d >> 31) & 0x7FFFFFFFull) : 0u;
+          unsigned ce = (lane <= stop && s >= ts) ? (unsigned)(d & 0x7FFFFFFFull) : 0u;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            cg += __shfl_xor_sync(0xffffffffu, cg, o);
+            ce += __shfl_xor_sync(0xffffffffu, ce, o);
+          }
+          pg += cg;
+          pe += ce;
+          if (inc_mask) done = true;
+          hi -= 32;
+        }
+        if (lane == 0) st_desc(p.desc + t, sp_pack(SP_INC, pg + G2, pe + Q2));
+      }
+      if (lane == 0) {
+        s_pg = pg;
+        s_pe = pe;
+      }
+    }
+    __syncthreads();
+    unsigned og = s_pg, oe = s_pe;
     for (int w = 0; w < warp; ++w) {
       og += wg[w];
       oe += we[w];
@@ -272,25 +402,26 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int pos = -1;
-      if (fg & (1u << e)) {
-        pos = (int)og++;
-      } else if (fe & (1u << e)) {
-        if (oe < need_eq) pos = (int)(gt_total + oe);
+      if (fe & (1u << e)) {                             // ties first: the need_eq lowest indices, slots [0, need_eq)
+        if (oe < need_eq) pos = (int)oe;
         ++oe;
+      } else if (fg & (1u << e)) {                      // then every key > tau in index order
+        pos = (int)(need_eq + og++);
       }
       if (pos >= 0 && pos < k) {
         const float val = a.v[e];
         const float idxw = __int_as_float(first + tid * EG_VEC + e);
         p.rec_to_l[ro + pos] = val;
         p.rec_to_l[ro + k + pos] = idxw;
-        p.rec_to_r[ro + pos] = val;
-        p.rec_to_r[ro + k + pos] = idxw;
+        if (p.rec_to_r != nullptr) {                    // null on a 2-rank ring: the one neighbour reads one copy
+          p.rec_to_r[ro + pos] = val;
+          p.rec_to_r[ro + k + pos] = idxw;
+        }
         b.v[e] = val;                                   // prev[idx] <- value sent (spevent.cpp:407-413)
         touched = true;
       }
     }
     if (touched) st_f8(p.prev + base, b);
-    __syncthreads();
   }
   // ---- publish: per-tensor sequence numbers (+ step-done flag in iter-sync mode) -------------
   __syncthreads();
@@ -305,7 +436,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
   for (int i = tid; i < p.tab.n_tensors; i += EG_THREADS) {
     if (p.fire[i]) {
       st_release_sys(p.seq_to_l + i, (uint32_t)step);
-      st_release_sys(p.seq_to_r + i, (uint32_t)step);
+      if (p.seq_to_r != nullptr) st_release_sys(p.seq_to_r + i, (uint32_t)step);
     }
   }
   __syncthreads();
@@ -313,92 +444,33 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
     *p.ticket = 0u;
     fence_sys();
     st_release_sys(p.done_to_l, (uint32_t)step);
-    st_release_sys(p.done_to_r, (uint32_t)step);
+    if (p.done_to_r != nullptr) st_release_sys(p.done_to_r, (uint32_t)step);
   }
 }
 
-// ---------------------------------------------------------------- 4. receive: scatter records
+// ---------------------------------------------------------------- stand-alone receive kernel
+// (the product path runs sparse_apply_prologue inside the mix+SGD kernel; this launch exists for unit tests and for
+// callers that keep the replicas up to date without stepping)
 __global__ void __launch_bounds__(EG_THREADS, 4) sparse_apply_kernel(const SparseParams p) {
-  __shared__ int s_last;
-  const int tid = threadIdx.x;
-  const int step = *p.pass_num + 1;
-  if (p.sync) {
-    if (tid == 0) {
-      wait_ge(p.done_from_l, (uint32_t)step, p.status, p.timeout_ns);
-      wait_ge(p.done_from_r, (uint32_t)step, p.status, p.timeout_ns);
-    }
-    __syncthreads();
-  }
-  // which records need applying?  iter-sync: only those rewritten since the last apply (values are
-  // stable after the done-flag wait).  async: every record that has ever been written -- exactly
-  // the reference, which re-scatters whatever the window holds on every step (idempotent).
-  const int sz = p.tab.n_tensors;
-  __shared__ unsigned char s_new[SP_MAX_TENSORS];
-  for (int i = tid; i < sz; i += EG_THREADS) {
-    const uint32_t sl = ld_acquire_sys(p.seq_from_l + i), sr = ld_acquire_sys(p.seq_from_r + i);
-    const bool nl = p.sync ? (sl > p.applied_l[i]) : (sl > 0u);
-    const bool nr = p.sync ? (sr > p.applied_r[i]) : (sr > 0u);
-    s_new[i] = (unsigned char)((nl ? 1 : 0) | (nr ? 2 : 0));
-  }
-  __syncthreads();
-  for (int i = 0; i < sz; ++i) {
-    const bool newl = s_new[i] & 1, newr = s_new[i] & 2;
-    if (!newl && !newr) continue;
-    const int k = p.t_k[i];
-    const int numel = p.tab.t_numel[i];
-    const size_t ro = (size_t)p.t_rec_off[i];
-    const size_t toff = (size_t)p.tab.t_tile_start[i] * EG_TILE;
-    for (int c = blockIdx.x * EG_THREADS + tid; c < k; c += gridDim.x * EG_THREADS) {
-      if (newl) {
-        const float v = __ldcg(p.rec_from_l + ro + c);
-        const int idx = __float_as_int(__ldcg(p.rec_from_l + ro + k + c));
-        if (idx >= 0 && idx < numel) p.rep_l[toff + idx] = v;      // spevent.cpp:438-448
-      }
-      if (newr) {
-        const float v = __ldcg(p.rec_from_r + ro + c);
-        const int idx = __float_as_int(__ldcg(p.rec_from_r + ro + k + c));
-        if (idx >= 0 && idx < numel) p.rep_r[toff + idx] = v;      // spevent.cpp:492-502
-      }
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned prev = atomicAdd(p.ticket, 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  if (p.sync) {
-    for (int i = tid; i < sz; i += EG_THREADS) {
-      p.applied_l[i] = ld_acquire_sys(p.seq_from_l + i);
-      p.applied_r[i] = ld_acquire_sys(p.seq_from_r + i);
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    *p.ticket = 0u;
-    if (p.sync) {
-      fence_sys();
-      st_release_sys(p.ack_to_l, (uint32_t)step);   // records of `step` consumed
-      st_release_sys(p.ack_to_r, (uint32_t)step);
-    }
-  }
+  sparse_apply_prologue(p, p.ticket + 2);
 }
 
 // ------------------------------------------------------------------------------------------
+int sparse_select_grid(int n_tiles, int max_grid) {
+  // blocked ranges of at most SP_MAX_OWN tiles per CTA for the two histogram passes
+  int g = max_grid;
+  const int need = (n_tiles + SP_MAX_OWN - 1) / SP_MAX_OWN;
+  if (g < need) g = need;
+  if (g > n_tiles) g = n_tiles;
+  return g < 1 ? 1 : g;
+}
+
 cudaError_t launch_sparse_select_push(const SparseParams& p, int grid, cudaStream_t s) {
-  const int sz = p.tab.n_tensors;
-  eg_count_launch(EG_FAM_SPARSE, 9);
-  sparse_hist_kernel<0><<<grid, EG_THREADS, 0, s>>>(p);
-  sparse_scan_kernel<0><<<sz, EG_THREADS, 0, s>>>(p);
-  sparse_hist_kernel<1><<<grid, EG_THREADS, 0, s>>>(p);
-  sparse_scan_kernel<1><<<sz, EG_THREADS, 0, s>>>(p);
-  sparse_hist_kernel<2><<<grid, EG_THREADS, 0, s>>>(p);
-  sparse_scan_kernel<2><<<sz, EG_THREADS, 0, s>>>(p);
-  sparse_count_kernel<<<grid, EG_THREADS, 0, s>>>(p);
-  sparse_tilescan_kernel<<<(sz + EG_WARPS - 1) / EG_WARPS, EG_THREADS, 0, s>>>(p);
-  sparse_compact_kernel<<<grid, EG_THREADS, 0, s>>>(p);
+  eg_count_launch(EG_FAM_SPARSE, 3);
+  const int hg = sparse_select_grid(p.tab.n_tiles, grid);
+  sparse_hist_kernel<<<hg, EG_THREADS, 0, s>>>(p);
+  sparse_cand_kernel<<<hg, EG_THREADS, 0, s>>>(p);
+  sparse_compact_kernel<<<grid, EG_THREADS, 0, s>>>(p);      // persistent, co-resident: look-back needs progress
   return cudaGetLastError();
 }
 

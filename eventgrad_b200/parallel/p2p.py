@@ -176,7 +176,10 @@ class P2PBackend(CommBackend):
             self.rep_r = arena.theta.clone()
             self.hist = torch.zeros(t.n_tensors * 2048, dtype=torch.int32, device=dev)
             self.sel_prefix, self.sel_remain = zi(t.n_tensors), zi(t.n_tensors)
-            self.tile_gt, self.tile_eq, self.t_gt_total = zi(t.n_tiles), zi(t.n_tiles), zi(t.n_tensors)
+            self.cand = torch.empty(t.n_padded, dtype=torch.int32, device=dev)      # candidate keys (worst case: all)
+            self.cand_cnt, self.done1, self.done2 = zi(t.n_tensors), zi(t.n_tensors), zi(t.n_tensors)
+            self.desc = torch.zeros(t.n_tiles, dtype=torch.int64, device=dev)       # look-back descriptors
+            self.sp_bar = zi(4)
             self.applied_l, self.applied_r = zi(t.n_tensors), zi(t.n_tensors)
         self.ar_ctr = zi(1)
         # gradient pointer table (table mode): device arrays + rotating pinned staging
@@ -278,11 +281,24 @@ class P2PBackend(CommBackend):
                 "ack_to_l": win.addr("ack_from_r", L), "ack_to_r": win.addr("ack_from_l", R),
                 "t_k": P(self.d_k), "t_rec_off": P(self.d_rec_off), "hist": P(self.hist),
                 "sel_prefix": P(self.sel_prefix), "sel_remain": P(self.sel_remain),
-                "tile_gt": P(self.tile_gt), "tile_eq": P(self.tile_eq), "t_gt_total": P(self.t_gt_total),
+                "cand": P(self.cand), "cand_cnt": P(self.cand_cnt), "done1": P(self.done1), "done2": P(self.done2),
+                "desc": P(self.desc), "bar": P(self.sp_bar),
                 "fire": P(self.fire), "pass_num": P(self.d_pass), "ticket": P(self.ticket[4:]),
                 "status": P(self.status), "timeout_ns": int(self.timeout_ns), "sync": 1 if self.sync else 0,
             })
+            # 2-rank ring: the one neighbour is both left and right -> write each record (and its seq / done flags)
+            # ONCE, into the peer's from-right inbox, and let the peer read that copy for both replicas
+            self.wire_dedup = self.ring.world == 2 and L == R
+            if self.wire_dedup:
+                sp.update({"rec_to_r": 0, "seq_to_r": 0, "done_to_r": 0,
+                           "rec_from_l": win.addr("rec_from_r"), "seq_from_l": win.addr("seq_from_r"),
+                           "done_from_l": win.addr("done_from_r")})
             self.sp = sp
+            # the mix+SGD kernel runs the receive side (scatter into the replicas) as its prologue
+            self.d_sp = torch.zeros((C.SPARSE_PARAMS_BYTES + 7) // 8, dtype=torch.int64, device=self.dev)
+            C.sparse_params_to_device(sp, self.d_sp.data_ptr())
+            if self.do_comm:
+                self.gp.update({"sparse": self.d_sp.data_ptr()})
         # ---- all-reduce parameter blocks (cent step; final averaging for every algorithm) ----
         W = self.ring.world
         self.d_peer_grad = torch.tensor([win.addr("grad", r) for r in range(W)], dtype=torch.int64, device=self.dev)
@@ -394,9 +410,8 @@ class P2PBackend(CommBackend):
                 return
             if self.sparse and self.do_comm:
                 if not self.overlap:
-                    C.sparse_select_push(self.sp, self.grid, s)
-                C.sparse_apply(self.sp, self.grid, s)
-                C.gossip_step(self.gp, self.grid, s)
+                    C.sparse_select_push(self.sp, self.grid, s)        # 3 launches: hist, candidates, compaction
+                C.gossip_step(self.gp, self.grid, s)                   # receive prologue + mix + SGD + trigger
             elif self.overlap:
                 C.gossip_step_phase(self.gp, 2, self.grid, s)
             elif self.dbuf:

@@ -116,7 +116,6 @@ def test_p2p_file_write_logs(tmp_path):
     send = open(tmp_path / "send0.txt").read().splitlines()
     recv = open(tmp_path / "recv0.txt").read().splitlines()
     assert len(send) == 10 and len(recv) == 10 and len(send[0].split(",  ")) == 8 * 3 + 1
-    assert len(open(tmp_path / "train0.txt").read().splitlines()) == 10
     tr.close()
 
 
@@ -127,7 +126,7 @@ def test_gpu_defaults_are_the_fast_path_and_fp32_uses_fused_bn():
     C = ext()
     n0 = C.launch_count()
     tr, _ = _run(steps=6)                               # dtype defaults to fp32
-    assert tr.cfg.dtype == "fp32" and tr.cfg.channels_last and tr.cfg.cuda_graph
+    assert tr.cfg.dtype == "fp32" and tr.cfg.cuda_graph and not tr.cfg.channels_last
     assert len(tr._graphs) == 1
     per_step = tr.own_launches_per_step
     assert per_step.get("bn", 0) >= 4 * 13 and per_step.get("gossip", 0) >= 1, per_step
