@@ -58,17 +58,22 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--out", default="")
     ap.add_argument("--skip-nccl", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of row-name prefixes to run (default: everything)")
     a = ap.parse_args()
     env = init_distributed("cuda")
     W = env.world
     res = {"world": W, "model": a.model}
     base = dict(dataset="mnist", model=a.model, lr=1e-2, momentum=0.9)   # mnist => comm even at W=1 (self loop)
+    only = [x for x in a.only.split(",") if x]
+    want = lambda name: (not only) or any(name.startswith(o) for o in only)
 
     # ---- dense fused gossip (decent) -----------------------------------------------------------
     # "ack_*": single inbox slot + WAR ack (round-1 protocol); "dbuf": two slots, no ack (the default since round 2)
     for name, dbuf, kw in (("ack_v256", False, dict(vec256_push=True)), ("ack_v128", False, dict(vec256_push=False)),
                            ("ack_d1", False, dict(group_iters=1)), ("ack_d4", False, dict(group_iters=4)),
                            ("dbuf", None, dict()), ("dbuf_d4", None, dict(group_iters=4))):
+        if not want(f"gossip_dense_{name}"):
+            continue
         cfg = TrainConfig(algo="decent", sync_mode="iter", double_buffer=dbuf, **base).validate()
         arena, be = make(cfg, env, a.model, **kw)
         assert be.dbuf == (dbuf is None)
@@ -85,6 +90,8 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- push-only kernel (phase 1): the ceiling of SM-issued NVLink stores, vs grid size ----------
+    if only and not want("push"):
+        return finish(res, env, a)
     cfg = TrainConfig(algo="decent", sync_mode="iter", overlap_push=True, **base).validate()
     arena, be = make(cfg, env, a.model)
     n_bytes = arena.table.n_elems * 4
@@ -182,6 +189,10 @@ def main():
             be.step()
         res["gossip_dense_nccl_baseline"] = {"ms": timed(st, env, max(10, a.iters // 2))}
 
+    finish(res, env, a)
+
+
+def finish(res, env, a):
     if env.rank == 0:
         print(json.dumps(res, indent=1))
         if a.out:

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--topk", default="10")
     ap.add_argument("--sync-mode", default="iter")
     ap.add_argument("--train-samples", type=int, default=0)
+    ap.add_argument("--dtype", default="", help="default: bf16 for the CIFAR programs (the 20-epoch schedule x many "
+                    "configurations is a GPU-minutes question), fp32 for MNIST")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     env = init_distributed("cuda")
@@ -45,8 +47,7 @@ def main():
     for hz in [float(x) for x in a.horizons.split(",")]:
         for tk in topks:
             kw = dict(backend="p2p", device="cuda", horizon=hz, thres_type=1, quiet=True, sync_mode=a.sync_mode,
-                      train_samples=ntr, cuda_graph=(ds == "cifar10"), channels_last=(ds == "cifar10"),
-                      dtype="bf16" if ds == "cifar10" else "fp32")
+                      train_samples=ntr, dtype=a.dtype or ("bf16" if ds == "cifar10" else "fp32"))
             if a.epochs:
                 kw["epochs"] = a.epochs
             if tk is not None:
@@ -58,6 +59,7 @@ def main():
             res = tr.finalize(evaluate=True)
             tr.backend.check_status()
             row = {"program": a.program, "world": env.world, "horizon": hz, "topk_percent": tk,
+                   "sync_mode": a.sync_mode, "dtype": cfg.dtype,
                    "epochs": cfg.epochs, "steps": res["steps"], "events_total": res["events_total"],
                    "dense_messages": res["dense_messages"], "messages_saved": res["messages_saved"],
                    "bytes_sent_rank0": res["bytes_sent_rank"], "train_acc_last_epoch": getattr(tr, "last_train_acc", None),

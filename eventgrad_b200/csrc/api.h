@@ -234,6 +234,9 @@ struct BnParams {
   int fused_ok;               // allow the single-launch fused path when the grid is co-resident
 };
 int bn_partial_rows(int sm_count);
+// fp32 NCHW variant (csrc/bn_nchw.cu): `hw` = H*W (multiple of 4), p.M = N*H*W.  Workspace: p.partial >= C*64*2
+// floats, p.ticket >= C words (p.flag / p.epoch unused).
+cudaError_t launch_bn_nchw(const BnParams& p, int hw, int which, int sm_count, cudaStream_t s);
 // which: 0 training forward, 1 apply only (eval), 2 backward
 cudaError_t launch_bn(const BnParams& p, int which, int sm_count, cudaStream_t s);
 

@@ -203,7 +203,7 @@ PYBIND11_MODULE(_C, m) {
                          uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt, uintptr_t partial,
                          uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
                          float eps, float momentum, int relu, int training, int fused_ok, int sm_count, int fp32,
-                         uintptr_t s) {
+                         int nchw_hw, uintptr_t s) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
     p.fp32 = fp32;
@@ -223,12 +223,15 @@ PYBIND11_MODULE(_C, m) {
     p.epoch = reinterpret_cast<unsigned int*>(epoch);
     p.status = reinterpret_cast<int*>(status);
     p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu; p.fused_ok = fused_ok;
-    check(launch_bn(p, training ? 0 : 1, sm_count, S(s)), "bn_forward");
+    if (nchw_hw > 0)
+      check(launch_bn_nchw(p, nchw_hw, training ? 0 : 1, sm_count, S(s)), "bn_forward (nchw)");
+    else
+      check(launch_bn(p, training ? 0 : 1, sm_count, S(s)), "bn_forward");
   });
   m.def("bn_backward", [](uintptr_t x, uintptr_t y, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
                           uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
                           uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
-                          int relu, int fused_ok, int sm_count, int fp32, uintptr_t s) {
+                          int relu, int fused_ok, int sm_count, int fp32, int nchw_hw, uintptr_t s) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
     p.fp32 = fp32;
@@ -248,7 +251,10 @@ PYBIND11_MODULE(_C, m) {
     p.epoch = reinterpret_cast<unsigned int*>(epoch);
     p.status = reinterpret_cast<int*>(status);
     p.M = M; p.C = C; p.relu = relu; p.fused_ok = fused_ok;
-    check(launch_bn(p, 2, sm_count, S(s)), "bn_backward");
+    if (nchw_hw > 0)
+      check(launch_bn_nchw(p, nchw_hw, 2, sm_count, S(s)), "bn_backward (nchw)");
+    else
+      check(launch_bn(p, 2, sm_count, S(s)), "bn_backward");
   });
   m.def("linear_tc", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int M, int N, int K, int relu,
                             int out_bf16, int sm_count, uintptr_t s) {

@@ -15,10 +15,10 @@
 //                           candidate list (one atomic per TILE, block-scan inside); the CTA that completes a
 //                           tensor resolves the remaining 21 bits (11 + 10) on that small list alone ->
 //                           exact threshold tau and the number of tau-ties to take.
-//   3. sparse_compact_kernel pass 3: single-pass ordered compaction with a decoupled look-back over the tiles of
-//                           each tensor (ties at tau resolved towards the lowest index => the selected SET is
-//                           deterministic), writing (value, int32 index) straight into BOTH neighbours' record
-//                           inboxes over NVLink and updating prev in the same pass.
+//   3. sparse_compact_kernel pass 3: compaction straight into BOTH neighbours' record inboxes over NVLink + prev
+//                           update: keys > tau take slots from one atomic per tile; ties at tau are resolved towards
+//                           the lowest index (the selected SET is deterministic) by a look-back over per-tile tie
+//                           counts that only tiles containing a tie perform.
 // The receive side (scatter of freshly arrived records into the replicas) is the PROLOGUE of the dense
 // mix+SGD kernel (gossip.cu, `sparse_apply_prologue` below + one grid barrier), so a spevent step is 4 launches.
 #include "sparse_apply.cuh"
@@ -136,7 +136,20 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const Sparse
     __syncthreads();
   };
   flush(-1);
+  // software pipeline: the loads of tile t+1 are in flight while the shared-memory atomics of tile t execute
+  F8 a, b, an, bn;
+  auto fetch = [&](int t, F8& x, F8& y) {
+    if (t < t1 && p.fire[p.tab.tile_tensor[t]]) {
+      const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+      x = ld_f8(p.theta + base);
+      y = ld_f8(p.prev + base);
+    }
+  };
+  fetch(t0, an, bn);
   for (int t = t0; t < t1; ++t) {
+    a = an;
+    b = bn;
+    fetch(t + 1, an, bn);
     const int i = p.tab.tile_tensor[t];
     if (tid == 0) p.desc[t] = 0ull;                      // look-back descriptors of pass 3 start EMPTY
     if (!p.fire[i]) continue;
@@ -145,8 +158,6 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const Sparse
       cur = i;
     }
     const int valid = tile_valid(p.tab, t, i);
-    const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
-    const F8 a = ld_f8(p.theta + base), b = ld_f8(p.prev + base);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (tid * EG_VEC + e >= valid) continue;
@@ -188,13 +199,23 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
   int per = (p.tab.n_tiles + G - 1) / G;
   if (per > SP_MAX_OWN) per = SP_MAX_OWN;
   const int t0 = min(p.tab.n_tiles, blockIdx.x * per), t1 = min(p.tab.n_tiles, t0 + per);
+  F8 a, b, an, bn;
+  auto fetch = [&](int t, F8& x, F8& y) {
+    if (t < t1 && p.fire[p.tab.tile_tensor[t]]) {
+      const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+      x = ld_f8(p.theta + base);
+      y = ld_f8(p.prev + base);
+    }
+  };
+  fetch(t0, an, bn);
   for (int t = t0; t < t1; ++t) {
+    a = an;
+    b = bn;
+    fetch(t + 1, an, bn);                                 // next tile's loads overlap this tile's scan + atomic
     const int i = p.tab.tile_tensor[t];
     if (!p.fire[i]) continue;
     const uint32_t prefix = p.sel_prefix[i];
     const int valid = tile_valid(p.tab, t, i);
-    const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
-    const F8 a = ld_f8(p.theta + base), b = ld_f8(p.prev + base);
     uint32_t keys[8];
     unsigned m = 0, c = 0;
 #pragma unroll
@@ -242,7 +263,17 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
     __syncthreads();
     for (int bkt = tid; bkt < SP_BINS; bkt += EG_THREADS) sh[bkt] = 0u;
     __syncthreads();
-    for (unsigned j = tid; j < n; j += EG_THREADS) atomicAdd(&sh[__ldcg(cand + j) >> 10], 1u);
+    for (unsigned j0 = 0; j0 < n; j0 += 8 * EG_THREADS) {           // 8 independent L2 loads in flight per thread
+      uint32_t cv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned j = j0 + u * EG_THREADS + tid;
+        cv[u] = (j < n) ? __ldcg(cand + j) : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (cv[u] != 0xFFFFFFFFu) atomicAdd(&sh[cv[u] >> 10], 1u);
+    }
     __syncthreads();
     unsigned d2, above;
     block_pick(sh, SP_BINS, remain, &d2, &above);
@@ -251,9 +282,16 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
     __syncthreads();
     for (int bkt = tid; bkt < 1024; bkt += EG_THREADS) sh[bkt] = 0u;
     __syncthreads();
-    for (unsigned j = tid; j < n; j += EG_THREADS) {
-      const uint32_t c = __ldcg(cand + j);
-      if ((c >> 10) == d2) atomicAdd(&sh[c & 0x3FFu], 1u);
+    for (unsigned j0 = 0; j0 < n; j0 += 8 * EG_THREADS) {
+      uint32_t cv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned j = j0 + u * EG_THREADS + tid;
+        cv[u] = (j < n) ? __ldcg(cand + j) : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (cv[u] != 0xFFFFFFFFu && (cv[u] >> 10) == d2) atomicAdd(&sh[cv[u] & 0x3FFu], 1u);
     }
     __syncthreads();
     unsigned d3;
@@ -261,18 +299,19 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
     if (tid == 0) {
       p.sel_prefix[i] = (p.sel_prefix[i] << 21) | (d2 << 10) | d3;    // tau: the k-th largest key, exactly
       p.sel_remain[i] = remain - above;                               // how many keys == tau are selected (>= 1)
+      p.cand_cnt[i] = 0u;                                             // pass 3 reuses it as the slot counter of keys > tau
     }
   }
 }
 
-// ---------------------------------------------------------------- 3. ordered compaction -> peers
-// Look-back descriptor of a tile: [63:62] state (1 = aggregate of this tile, 2 = inclusive prefix over the tensor's
-// tiles up to and including this one), [61:31] count(key > tau), [30:0] count(key == tau).
+// ---------------------------------------------------------------- 3. compaction -> peers
+// Slots of a tensor's record: [0, need_eq) the selected ties (keys == tau; the need_eq LOWEST indices win, so the
+// selected set is deterministic), then every key > tau.  Keys > tau take their slots from one atomic reservation per
+// tile (their order inside the record is irrelevant: the receiver scatters by index).  Ties are ordered by a
+// look-back over per-tile tie counts, performed only by tiles that contain a tie and cut short as soon as need_eq
+// earlier ties have been seen -- in the common case (one element equals tau) a single tile per tensor looks back.
+// Descriptor of a tile: [63:62] = 1 once published, [31:0] number of keys == tau in the tile.
 #define SP_AGG (1ull << 62)
-#define SP_INC (2ull << 62)
-__device__ __forceinline__ unsigned long long sp_pack(unsigned long long st, unsigned gt, unsigned eq) {
-  return st | ((unsigned long long)gt << 31) | (unsigned long long)eq;
-}
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -284,10 +323,11 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
 
 __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const SparseParams p) {
   __shared__ unsigned int wg[EG_WARPS], we[EG_WARPS];
-  __shared__ unsigned int s_pg, s_pe;                   // exclusive prefix of this tile inside its tensor
+  __shared__ unsigned int s_gbase, s_pe;                // slot base of this tile's keys > tau; ties before this tile
   __shared__ int s_last, s_ok;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int step = *p.pass_num + 1;
+  const int G = gridDim.x;
   if (p.sync) {
     if (tid == 0) {   // WAR guard on the neighbours' record inboxes
       bool ok = wait_ge(p.ack_from_l, (uint32_t)(step - 1), p.status, p.timeout_ns);
@@ -297,9 +337,21 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
     __syncthreads();
     if (!s_ok) return;                                  // wedged peer: store nothing (status is sticky)
   }
-  // tiles in ASCENDING order, strided over the persistent grid: tile t-1 is processed by the neighbouring CTA in
-  // the same round, so the look-back never waits on work that has not been scheduled (all CTAs co-resident)
-  for (int t = blockIdx.x; t < p.tab.n_tiles; t += gridDim.x) {
+  // tiles in ASCENDING order, strided over the persistent (co-resident) grid: a tile that has to look back only
+  // waits for tiles that are already being processed
+  F8 a, b, an, bn;
+  auto fetch = [&](int t, F8& x, F8& y) {
+    if (t < p.tab.n_tiles && p.fire[p.tab.tile_tensor[t]]) {
+      const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
+      x = ld_f8(p.theta + base);
+      y = ld_f8(p.prev + base);
+    }
+  };
+  fetch(blockIdx.x, an, bn);
+  for (int t = blockIdx.x; t < p.tab.n_tiles; t += G) {
+    a = an;
+    b = bn;
+    fetch(t + G, an, bn);                               // next tile's loads overlap this tile's scan / atomics
     const int i = p.tab.tile_tensor[t];
     if (!p.fire[i]) continue;
     const uint32_t tau = p.sel_prefix[i];
@@ -309,8 +361,6 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
     const int valid = tile_valid(p.tab, t, i);
     const int first = (t - ts) * EG_TILE;
     const size_t base = (size_t)t * EG_TILE + (size_t)tid * EG_VEC;
-    const F8 a = ld_f8(p.theta + base);
-    F8 b = ld_f8(p.prev + base);
     unsigned fg = 0, fe = 0, g = 0, q = 0;   // bit masks + counts
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -333,64 +383,50 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
         qi += vq;
       }
     }
-    __syncthreads();                                    // previous tile's readers of wg / s_pg are done
+    __syncthreads();                                    // previous tile's readers of wg / s_gbase are done
     if (lane == 31) {
       wg[warp] = gi;
       we[warp] = qi;
     }
     __syncthreads();
     if (warp == 0) {
-      // tile totals -> publish -> decoupled look-back over the preceding tiles of the SAME tensor (one warp,
-      // 32 descriptors per round) -> publish the inclusive prefix
       unsigned G2 = 0, Q2 = 0;
 #pragma unroll
       for (int w = 0; w < EG_WARPS; ++w) {
         G2 += wg[w];
         Q2 += we[w];
       }
-      unsigned pg = 0, pe = 0;
-      if (t == ts) {
-        if (lane == 0) st_desc(p.desc + t, sp_pack(SP_INC, G2, Q2));
-      } else {
-        if (lane == 0) st_desc(p.desc + t, sp_pack(SP_AGG, G2, Q2));
-        int hi = t - 1;                                 // next descriptor to inspect (descending)
+      if (lane == 0) {
+        st_desc(p.desc + t, SP_AGG | (unsigned long long)Q2);
+        s_gbase = G2 ? atomicAdd(p.cand_cnt + i, G2) : 0u;   // cand_cnt was reset by pass 2: slot counter here
+      }
+      unsigned pe = 0;
+      if (Q2 > 0 && t > ts) {                           // ties in this tile: how many ties precede it?
+        int hi = t - 1;
         const uint64_t t_start = globaltimer_ns();
-        bool done = false;
-        while (!done) {
-          const int s = hi - lane;
-          unsigned long long d = SP_INC;                // lanes below the tensor's first tile: neutral terminator
-          if (s >= ts) {
+        while (hi >= ts && pe < need_eq) {              // once need_eq earlier ties exist, nothing here is selected
+          const int s2 = hi - lane;
+          unsigned long long d = SP_AGG;                // lanes below the tensor's first tile: neutral
+          if (s2 >= ts) {
             do {
-              d = ld_desc(p.desc + s);
+              d = ld_desc(p.desc + s2);
               if ((d >> 62) == 0ull && globaltimer_ns() - t_start > p.timeout_ns) {   // never hang the GPU
                 atomicExch(p.status, EG_ERR_TIMEOUT);
-                d = SP_INC;
+                d = SP_AGG;
               }
             } while ((d >> 62) == 0ull);
           }
-          const unsigned inc_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-          const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 32;     // first lane (= nearest tile) holding a prefix
-          unsigned cg = (lane <= stop && s >= ts) ? (unsigned)((d >> 31) & 0x7FFFFFFFull) : 0u;
-          unsigned ce = (lane <= stop && s >= ts) ? (unsigned)(d & 0x7FFFFFFFull) : 0u;
+          unsigned ce = (s2 >= ts) ? (unsigned)(d & 0xFFFFFFFFull) : 0u;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            cg += __shfl_xor_sync(0xffffffffu, cg, o);
-            ce += __shfl_xor_sync(0xffffffffu, ce, o);
-          }
-          pg += cg;
+          for (int o = 16; o > 0; o >>= 1) ce += __shfl_xor_sync(0xffffffffu, ce, o);
           pe += ce;
-          if (inc_mask) done = true;
           hi -= 32;
         }
-        if (lane == 0) st_desc(p.desc + t, sp_pack(SP_INC, pg + G2, pe + Q2));
       }
-      if (lane == 0) {
-        s_pg = pg;
-        s_pe = pe;
-      }
+      if (lane == 0) s_pe = pe;
     }
     __syncthreads();
-    unsigned og = s_pg, oe = s_pe;
+    unsigned og = s_gbase, oe = s_pe;
     for (int w = 0; w < warp; ++w) {
       og += wg[w];
       oe += we[w];
@@ -402,10 +438,10 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_compact_kernel(const Spa
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int pos = -1;
-      if (fe & (1u << e)) {                             // ties first: the need_eq lowest indices, slots [0, need_eq)
+      if (fe & (1u << e)) {                             // ties: the need_eq lowest indices, slots [0, need_eq)
         if (oe < need_eq) pos = (int)oe;
         ++oe;
-      } else if (fg & (1u << e)) {                      // then every key > tau in index order
+      } else if (fg & (1u << e)) {                      // every key > tau
         pos = (int)(need_eq + og++);
       }
       if (pos >= 0 && pos < k) {

@@ -68,25 +68,37 @@ __device__ __forceinline__ void sparse_apply_prologue(const SparseParams& p, uns
     const bool nr = p.sync ? (sr > p.applied_r[i]) : (sr > 0u);
     s_new[i] = (unsigned char)((nl ? 1 : 0) | (nr ? 2 : 0));
   }
+  // record start (in records, not words) of every tensor -> shared memory, so a thread can map a flat record number
+  // to its tensor with a 10-step binary search; ALL records of ALL tensors are then spread evenly over the grid
+  // (a per-tensor loop left most CTAs idle and serialised ~86 dependent global round trips on CTA 0)
+  __shared__ int s_roff[SP_MAX_TENSORS + 1];
+  for (int i = tid; i < sz; i += EG_THREADS) s_roff[i] = p.t_rec_off[i] >> 1;
+  if (tid == 0) s_roff[sz] = (p.t_rec_off[sz - 1] >> 1) + p.t_k[sz - 1];
   __syncthreads();
-  for (int i = 0; i < sz; ++i) {
-    const bool newl = s_new[i] & 1, newr = s_new[i] & 2;
-    if (!newl && !newr) continue;
+  const int K = s_roff[sz];
+  for (int r = blockIdx.x * EG_THREADS + tid; r < K; r += gridDim.x * EG_THREADS) {
+    int lo = 0, hi = sz - 1;                             // last tensor with s_roff[i] <= r
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_roff[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    const int i = lo;
+    const unsigned char nw = s_new[i];
+    if (!nw) continue;
+    const int c = r - s_roff[i];
     const int k = p.t_k[i];
     const int numel = p.tab.t_numel[i];
     const size_t ro = (size_t)p.t_rec_off[i];
     const size_t toff = (size_t)p.tab.t_tile_start[i] * EG_TILE;
-    for (int c = blockIdx.x * EG_THREADS + tid; c < k; c += gridDim.x * EG_THREADS) {
-      if (newl) {
-        const float v = __ldcg(p.rec_from_l + ro + c);
-        const int idx = __float_as_int(__ldcg(p.rec_from_l + ro + k + c));
-        if (idx >= 0 && idx < numel) p.rep_l[toff + idx] = v;
-      }
-      if (newr) {
-        const float v = __ldcg(p.rec_from_r + ro + c);
-        const int idx = __float_as_int(__ldcg(p.rec_from_r + ro + k + c));
-        if (idx >= 0 && idx < numel) p.rep_r[toff + idx] = v;
-      }
+    if (nw & 1) {
+      const float v = __ldcg(p.rec_from_l + ro + c);
+      const int idx = __float_as_int(__ldcg(p.rec_from_l + ro + k + c));
+      if (idx >= 0 && idx < numel) p.rep_l[toff + idx] = v;      // spevent.cpp:438-448
+    }
+    if (nw & 2) {
+      const float v = __ldcg(p.rec_from_r + ro + c);
+      const int idx = __float_as_int(__ldcg(p.rec_from_r + ro + k + c));
+      if (idx >= 0 && idx < numel) p.rep_r[toff + idx] = v;      // spevent.cpp:492-502
     }
   }
   const bool last = grid_barrier_arrive(bar, &s_gen);

@@ -33,11 +33,28 @@ def _workspace(device):
               "f": (ctl[0:].data_ptr(), ctl[128:].data_ptr(), ctl[192:].data_ptr()),
               "b": (ctl[64:].data_ptr(), ctl[160:].data_ptr(), ctl[200:].data_ptr()),
               "status": ctl[256:].data_ptr(), "C": C,
+              # fp32 NCHW kernels (csrc/bn_nchw.cu): per-channel tickets (forward | backward) + partial pairs
+              "nchw_ticket": torch.zeros(2 * 2048, dtype=torch.int32, device=device),
+              "nchw_partial": torch.empty(2048 * 64 * 2, dtype=torch.float32, device=device),
               # single-launch (spin-flag) variant for small tensors: measured SLOWER than the two-launch
               # split path inside a CUDA graph (1.52 vs 1.42 ms/step at batch 32), so it is opt-in
               "fused": 1 if os.environ.get("EGB_BN_FUSED_SMALL", "0") == "1" else 0}
         _WS[device] = ws
     return ws
+
+
+def _eligible_nchw(x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
+    """fp32 NCHW path (csrc/bn_nchw.cu): the layout of the reference-precision run (cuDNN's fp32 convs are NCHW)."""
+    if os.environ.get("EGB_FUSED_BN", "1") == "0":
+        return False
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()):
+        return False
+    hw = x.shape[2] * x.shape[3]
+    if hw % 4 or x.shape[1] > 2048 or x.numel() == 0:
+        return False
+    if residual is not None and not (residual.dtype == x.dtype and residual.shape == x.shape and residual.is_contiguous()):
+        return False
+    return True
 
 
 def _eligible(x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
@@ -75,12 +92,16 @@ class _FusedBNActFn(torch.autograd.Function):
             invstd = torch.rsqrt(running_var + eps)
             rm = rv = nb = 0
         stream = torch.cuda.current_stream(x.device).cuda_stream
+        nchw = not _eligible(x, residual)              # caller guarantees one of the two layouts is eligible
+        ctx.nchw_hw = H * W if nchw else 0
         with torch.cuda.device(x.device):
             C_ext.bn_forward(x.data_ptr(), residual.data_ptr() if residual is not None else 0, y.data_ptr(),
                              weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm, rv, nb,
-                             ws["partial"].data_ptr(), ws["f"][0], ws["f"][1], ws["f"][2], ws["status"], M, C,
+                             (ws["nchw_partial"] if nchw else ws["partial"]).data_ptr(),
+                             ws["nchw_ticket"].data_ptr() if nchw else ws["f"][0], ws["f"][1], ws["f"][2],
+                             ws["status"], M, C,
                              float(eps), float(momentum), 1 if relu else 0, 1 if training else 0, ws["fused"],
-                             ws["sm"], 1 if x.dtype == torch.float32 else 0, stream)
+                             ws["sm"], 1 if x.dtype == torch.float32 else 0, ctx.nchw_hw, stream)
         ctx.save_for_backward(x, y, weight, mean, invstd)
         ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
         return y
@@ -94,7 +115,10 @@ class _FusedBNActFn(torch.autograd.Function):
         C_ext = ws["C"]
         N, C, H, W = x.shape
         M = N * H * W
-        if dy.dtype != x.dtype or not dy.is_contiguous(memory_format=torch.channels_last):
+        if ctx.nchw_hw:
+            if dy.dtype != x.dtype or not dy.is_contiguous():
+                dy = dy.to(x.dtype).contiguous()
+        elif dy.dtype != x.dtype or not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
@@ -104,9 +128,11 @@ class _FusedBNActFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                               dres.data_ptr() if dres is not None else 0, weight.data_ptr(), mean.data_ptr(),
-                              invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws["partial"].data_ptr(),
-                              ws["b"][0], ws["b"][1], ws["b"][2], ws["status"], M, C, 1 if ctx.relu else 0,
-                              ws["fused"], ws["sm"], 1 if x.dtype == torch.float32 else 0, stream)
+                              invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                              (ws["nchw_partial"] if ctx.nchw_hw else ws["partial"]).data_ptr(),
+                              ws["nchw_ticket"][2048:].data_ptr() if ctx.nchw_hw else ws["b"][0], ws["b"][1], ws["b"][2],
+                              ws["status"], M, C, 1 if ctx.relu else 0,
+                              ws["fused"], ws["sm"], 1 if x.dtype == torch.float32 else 0, ctx.nchw_hw, stream)
         return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
 
 
@@ -121,7 +147,7 @@ def bn_act_reference(x, weight, bias, running_mean, running_var, residual, train
 class FusedBNAct(nn.BatchNorm2d):
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
         training = self.training or (self.running_mean is None)
-        if _eligible(x, residual) and self.affine and self.momentum is not None:
+        if (_eligible(x, residual) or _eligible_nchw(x, residual)) and self.affine and self.momentum is not None:
             return _FusedBNActFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
                                        self.num_batches_tracked if training else None, residual, training,
                                        self.momentum, self.eps, relu)

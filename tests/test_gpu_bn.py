@@ -131,10 +131,36 @@ def test_single_launch_variant_matches_split(monkeypatch):
 @pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False), (False, True)])
 @pytest.mark.parametrize("fused_small", [0, 1])
 def test_fused_bn_act_fp32(shape, relu, res, fused_small):
+    _fp32_case(shape, relu, res, fused_small, torch.channels_last)
+
+
+# fp32 NCHW kernels (csrc/bn_nchw.cu) -- the layout of the reference-precision default path.  Includes channel counts
+# that are not a multiple of 64 and an H*W whose float4 count is not a power of two (division path).
+@pytest.mark.parametrize("shape", [(32, 64, 32, 32), (7, 128, 16, 16), (5, 256, 8, 8), (3, 512, 4, 4), (4, 10, 6, 6),
+                                   (256, 64, 32, 32), (64, 128, 16, 16), (1, 3, 2, 2), (2, 2048, 2, 2), (9, 20, 12, 12)])
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False), (False, True)])
+def test_fused_bn_act_fp32_nchw(shape, relu, res):
+    _fp32_case(shape, relu, res, 0, torch.contiguous_format)
+
+
+def test_fused_bn_nchw_eval_mode():
+    x = torch.randn(4, 128, 8, 8, device="cuda")
+    r = torch.randn(4, 128, 8, 8, device="cuda")
+    bn = FusedBNAct(128).cuda()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.2)
+        bn.running_var.uniform_(0.5, 2.0)
+    bn.eval()
+    y = bn(x, residual=r, relu=True)
+    yb = bn_act_reference(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, r, False, 0.1, bn.eps, True)
+    torch.testing.assert_close(y, yb, rtol=1e-5, atol=1e-5)
+
+
+def _fp32_case(shape, relu, res, fused_small, fmt):
     import eventgrad_b200.ops.bn_act as B
     N, C, H, W = shape
     g = torch.Generator(device="cuda").manual_seed(1)
-    mk = lambda s, b: (torch.randn(N, C, H, W, generator=g, device="cuda") * s + b).contiguous(memory_format=torch.channels_last)
+    mk = lambda s, b: (torch.randn(N, C, H, W, generator=g, device="cuda") * s + b).contiguous(memory_format=fmt)
     x, r, dy = mk(1.5, 0.3), mk(1.0, 0.0), mk(1.0, 0.0)
     B._workspace(x.device)["fused"] = fused_small
     try:
@@ -146,9 +172,11 @@ def test_fused_bn_act_fp32(shape, relu, res, fused_small):
         ref.load_state_dict(bn.state_dict())
         xa = x.clone().requires_grad_(True)
         ra = r.clone().requires_grad_(True) if res else None
-        assert _eligible(xa, ra)
+        assert _eligible(xa, ra) if fmt == torch.channels_last else B._eligible_nchw(xa, ra)
+        n0 = B._workspace(x.device)["C"].launch_counts()["bn"]
         y = bn(xa, residual=ra, relu=relu)
-        assert y.dtype == torch.float32 and y.is_contiguous(memory_format=torch.channels_last)
+        assert B._workspace(x.device)["C"].launch_counts()["bn"] > n0          # the CUDA path ran, not the fallback
+        assert y.dtype == torch.float32 and y.is_contiguous(memory_format=fmt)
         y.backward(dy)
         xb = x.clone().requires_grad_(True)
         rb = r.clone().requires_grad_(True) if res else None
@@ -203,34 +231,79 @@ def _plain_run(steps, batches, theta0_model, channels_last, lr, mu):
     return torch.stack(out).cpu()
 
 
-def test_fp32_first_step_gradients_match_plain_pytorch():
-    """Same weights, same batch: the default GPU path (NHWC, fused fp32 BN kernels) and a plain PyTorch NCHW model give
-    the same loss and the same gradients to fp32 accuracy."""
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_fp32_first_step_gradients_vs_fp64_truth(nhwc):
+    """Same weights, same batch.  Ground truth = the same network in float64 (plain PyTorch).  The fused fp32 BN kernels
+    (NCHW = default fp32 layout, and NHWC) must be as close to it as plain PyTorch fp32 (cuDNN BN + ATen add/ReLU) is:
+    two fp32 evaluations differ by ReLU-boundary flips (an element whose pre-activation is +1e-7 in one run and -1e-7 in
+    the other flips a whole gradient term), so fp32-vs-fp32 is the wrong yardstick -- distance to fp64 is the right one."""
     import os
     import torch.nn.functional as F
     from eventgrad_b200.models import build_model
+    from eventgrad_b200.ops import ext
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     a = build_model("resnet18").cuda().train()
     b = build_model("resnet18").cuda().train()
+    t = build_model("resnet18").cuda().train()
     b.load_state_dict(a.state_dict())
-    a = a.to(memory_format=torch.channels_last)
+    t.load_state_dict(a.state_dict())
+    t = t.double()
+    if nhwc:
+        a = a.to(memory_format=torch.channels_last)
     x = torch.randn(32, 3, 32, 32, device="cuda")
     y = torch.randint(0, 10, (32,), device="cuda")
-    la = F.cross_entropy(a(x.contiguous(memory_format=torch.channels_last)), y)
+    n0 = ext().launch_counts()["bn"]
+    la = F.cross_entropy(a(x.contiguous(memory_format=torch.channels_last) if nhwc else x), y)
     la.backward()
+    assert ext().launch_counts()["bn"] - n0 == 4 * 28          # every BN layer took the fused CUDA path
     os.environ["EGB_FUSED_BN"] = "0"
     try:
         lb = F.cross_entropy(b(x), y)
         lb.backward()
+        lt = F.cross_entropy(t(x.double()), y)
+        lt.backward()
     finally:
         os.environ["EGB_FUSED_BN"] = "1"
-    assert abs(float(la) - float(lb)) < 1e-5
-    ga = torch.cat([p.grad.flatten() for p in a.parameters()])
-    gb = torch.cat([p.grad.flatten() for p in b.parameters()])
-    rel = float((ga - gb).norm() / gb.norm())
-    assert rel < 2e-4, rel
+    cat = lambda m: torch.cat([p.grad.detach().double().flatten() for p in m.parameters()])
+    ga, gb, gt = cat(a), cat(b), cat(t)
+    err_ours = float((ga - gt).norm() / gt.norm())
+    err_plain = float((gb - gt).norm() / gt.norm())
+    print(f"fp32 gradient error vs fp64 truth: fused BN ({'NHWC' if nhwc else 'NCHW'}) {err_ours:.3e}, plain PyTorch {err_plain:.3e}; "
+          f"loss error {abs(float(la) - float(lt)):.2e} vs {abs(float(lb) - float(lt)):.2e}")
+    assert abs(float(la.detach()) - float(lt.detach())) < 1e-5
+    assert err_ours <= 3.0 * err_plain + 1e-5, (err_ours, err_plain)
+
+
+@pytest.mark.parametrize("fmt", [torch.contiguous_format, torch.channels_last])
+@pytest.mark.parametrize("shape", [(32, 512, 4, 4), (32, 64, 32, 32), (16, 128, 16, 16)])
+def test_fp32_bn_statistics_vs_fp64(shape, fmt):
+    """No ReLU (no mask discontinuity): y, dx and the fp32 statistics dgamma / dbeta / mean / var of the fused fp32
+    kernels against a float64 evaluation of the same op -- errors at the fp32 rounding level (1e-6), tighter than
+    what cuDNN's own fp32 BN achieves on the same inputs."""
+    N, C, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mk = lambda s, b: (torch.randn(N, C, H, W, generator=g, device="cuda") * s + b).contiguous(memory_format=fmt)
+    x, r, dy = mk(1.5, 0.7), mk(1.0, 0.0), mk(1.0, 0.1)
+    bn = FusedBNAct(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    ref = torch.nn.BatchNorm2d(C).cuda().train().double()
+    ref.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in bn.state_dict().items()})
+    xa, ra = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    y = bn(xa, residual=ra, relu=False)
+    y.backward(dy)
+    xb, rb = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    yb = ref(xb) + rb
+    yb.backward(dy.double())
+    rel = lambda u, v: float((u.double() - v).norm() / v.norm())
+    assert rel(y, yb) < 2e-6 and rel(xa.grad, xb.grad) < 5e-6
+    assert rel(bn.weight.grad, ref.weight.grad) < 2e-6, rel(bn.weight.grad, ref.weight.grad)
+    assert rel(bn.bias.grad, ref.bias.grad) < 2e-6, rel(bn.bias.grad, ref.bias.grad)
+    assert rel(bn.running_mean, ref.running_mean) < 2e-6 and rel(bn.running_var, ref.running_var) < 2e-6
+    assert torch.equal(ra.grad, dy)                              # dres is dz itself
 
 
 def test_fp32_training_tracks_plain_pytorch_50_steps():

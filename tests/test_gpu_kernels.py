@@ -179,6 +179,37 @@ def test_spevent_vs_simulator(R, pct):
     w.close()
 
 
+@pytest.mark.parametrize("R", [2, 3])
+@pytest.mark.parametrize("pct", [1.0, 10.0, 37.0])
+def test_spevent_heavy_ties_resolved_towards_lowest_index(R, pct):
+    """Three-valued gradients => thousands of EQUAL |theta - prev| keys per tensor, so the k-th largest key sits inside
+    a big tie group spanning many tiles: exercises the exact-threshold select (candidate bucket = almost everything),
+    the tie look-back across tiles and the 'lowest index wins' rule -- bitwise vs the oracle (stable sort)."""
+    cfg = _cfg("spevent", topk_percent=pct, initial_comm_passes=3, horizon=1.0, momentum=0.0)
+    w = _world(cfg, R)
+    t = w.arenas[0].table
+    sim = RingSimulator(R, w.arenas[0].theta.cpu(), t, "spevent", TriggerConfig.from_train(cfg), lr=cfg.lr,
+                        momentum=0.0, topk_percent=pct)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for s in range(8):
+        fires = [be.fire.clone().bool() for be in w.backends]
+        g = []
+        for r in range(R):
+            u = torch.rand(t.n_padded, generator=gen, device="cuda")
+            g.append(torch.where(u < 0.3, -0.0625, torch.where(u < 0.6, 0.0, 0.0625)).to(torch.float32))
+        g = _mask_pad(w, g)
+        w.step(g)
+        sim.step([x.cpu() for x in g], fires=fires)
+    torch.cuda.synchronize()
+    for r, be in enumerate(w.backends):
+        be.check_status()
+        assert torch.equal(be.prev.cpu(), sim.prev[r]), f"prev rank {r}"
+        assert torch.equal(be.rep_l.cpu(), sim.rep_l[r]), f"rep_l rank {r}"
+        assert torch.equal(be.rep_r.cpu(), sim.rep_r[r]), f"rep_r rank {r}"
+        assert torch.equal(w.arenas[r].theta.cpu(), sim.theta[r]), f"theta rank {r}"
+    w.close()
+
+
 @pytest.mark.parametrize("R", [2, 4])
 @pytest.mark.parametrize("model", ["mlp", "resnet18"])
 def test_cent_allreduce_vs_reference(R, model):
