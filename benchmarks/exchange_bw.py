@@ -27,6 +27,10 @@ from eventgrad_b200.parallel.p2p import P2PBackend, preallocate_arena_buffers  #
 from eventgrad_b200.utils.dist import barrier, init_distributed, max_over_ranks, shutdown  # noqa: E402
 
 
+NVL = None          # NvlinkCounters of this rank's GPU (set in main)
+LAST_NVLINK = {}    # measured NVLink bytes per launch of the most recent timed() call (this rank)
+
+
 def timed(fn, env, iters, warm=5):
     for _ in range(warm):
         fn()
@@ -34,11 +38,16 @@ def timed(fn, env, iters, warm=5):
     barrier(env)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    c0 = NVL.read() if (NVL is not None and NVL.ok) else None
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
+    c1 = NVL.read() if c0 is not None else None
+    LAST_NVLINK.clear()
+    if c0 is not None and c1 is not None:
+        LAST_NVLINK.update({"nvlink_" + k + "_bytes_per_launch_measured": (c1[k] - c0[k]) / iters for k in c0})
     barrier(env)
     return max_over_ranks(e0.elapsed_time(e1), env) / iters
 
@@ -62,7 +71,10 @@ def main():
     a = ap.parse_args()
     env = init_distributed("cuda")
     W = env.world
-    res = {"world": W, "model": a.model}
+    global NVL
+    from eventgrad_b200.utils.clocks import NvlinkCounters
+    NVL = NvlinkCounters(env.device.index or 0)
+    res = {"world": W, "model": a.model, "nvlink_counters": "NVML NVLINK_THROUGHPUT_{DATA,RAW}_{TX,RX}, rank 0's GPU" if NVL.ok else "unavailable"}
     base = dict(dataset="mnist", model=a.model, lr=1e-2, momentum=0.9)   # mnist => comm even at W=1 (self loop)
     only = [x for x in a.only.split(",") if x]
     want = lambda name: (not only) or any(name.startswith(o) for o in only)
@@ -84,7 +96,7 @@ def main():
         res[f"gossip_dense_{name}"] = {"ms": ms, "egress_GBps_per_gpu": wire / ms / 1e6,
                                       "frac_of_770": wire / ms / 1e6 / 770, "frac_of_900": wire / ms / 1e6 / 900,
                                       "wire_bytes_per_gpu": wire,
-                                      "hbm_GBps": 9 * arena.table.n_padded * 4 / ms / 1e6, "grid": be.grid}
+                                      "hbm_GBps": 9 * arena.table.n_padded * 4 / ms / 1e6, "grid": be.grid, **LAST_NVLINK}
         be.close()
         del arena, be
         torch.cuda.empty_cache()
@@ -115,7 +127,9 @@ def main():
     arena, be = make(cfg, env, a.model)
     n_bytes = arena.table.n_elems * 4
     ms = timed(be.step, env, a.iters)
-    res["event_async_allfire"] = {"ms": ms, "egress_GBps_per_gpu": 2 * n_bytes / ms / 1e6}
+    wire = (1 if be.wire_dedup else 2) * n_bytes
+    res["event_async_allfire"] = {"ms": ms, "egress_GBps_per_gpu": wire / ms / 1e6, "frac_of_770": wire / ms / 1e6 / 770,
+                                  "wire_bytes_per_gpu": wire, **LAST_NVLINK}
     be.close(); del arena, be; torch.cuda.empty_cache()
     cfg = TrainConfig(algo="event", sync_mode="iter", thres_type=0, constant=1e30, initial_comm_passes=0,
                       **base).validate()
@@ -134,8 +148,10 @@ def main():
             arena.grad.normal_(0, 0.01)
             be.step()
         ms = timed(stp, env, max(10, a.iters // 3))
+        nvl = dict(LAST_NVLINK)
         ms_g = timed(lambda: arena.grad.normal_(0, 0.01), env, 20)
-        res[f"spevent_{pct:g}pct"] = {"ms": ms - ms_g, "K": be.K}
+        res[f"spevent_{pct:g}pct"] = {"ms": ms - ms_g, "K": be.K, "launches_per_step": 4, **nvl,
+                                      "wire_bytes_per_gpu": (1 if be.wire_dedup else 2) * 2 * be.K * 4}
         be.check_status()
         be.close(); del arena, be; torch.cuda.empty_cache()
 
@@ -146,7 +162,7 @@ def main():
         n_bytes = arena.table.n_elems * 4
         ms = timed(be.step, env, a.iters)
         be.check_status()
-        entry = {"ms_fused": ms, "bytes": n_bytes,
+        entry = {"ms_fused": ms, "bytes": n_bytes, **LAST_NVLINK,
                  "busbw_GBps": (2 * (W - 1) / W) * n_bytes / ms / 1e6 if W > 1 else 0.0}
         if W > 1 and not a.skip_nccl:
             g = torch.zeros(arena.table.n_padded, device=env.device)

@@ -8,12 +8,12 @@
 // Device design, round 2: THREE launches, three streaming passes over (theta, prev), for ALL fired tensors of
 // the model at once (segmented by tensor: a tile belongs to exactly one tensor), nothing sorted, no host round
 // trip.  (Round 1 needed 9 launches / 5 passes and was as slow as the dense step it is meant to undercut.)
-//   1. sparse_hist_kernel   pass 1: shared-memory histogram of the top 11 bits of the monotone uint32 image of
+//   1. sparse_hist_kernel   pass 1: shared-memory histogram of bits [30:20] of the monotone uint32 image of
 //                           |diff|, merged per tensor; the CTA that completes a tensor picks the bucket that
 //                           holds the k-th largest key (no separate scan launch).
-//   2. sparse_cand_kernel   pass 2: the low 21 bits of every key in that bucket go to a compact per-tensor
+//   2. sparse_cand_kernel   pass 2: the low 20 bits of every key in that bucket go to a compact per-tensor
 //                           candidate list (one atomic per TILE, block-scan inside); the CTA that completes a
-//                           tensor resolves the remaining 21 bits (11 + 10) on that small list alone ->
+//                           tensor resolves the remaining 20 bits (11 + 9) on that small list alone ->
 //                           exact threshold tau and the number of tau-ties to take.
 //   3. sparse_compact_kernel pass 3: compaction straight into BOTH neighbours' record inboxes over NVLink + prev
 //                           update: keys > tau take slots from one atomic per tile; ties at tau are resolved towards
@@ -25,6 +25,11 @@
 
 namespace egb {
 
+// Radix digits of the key.  Keys are |x| bit patterns, so bit 31 is always 0: the first digit is bits [30:20]
+// (8 exponent + 3 mantissa bits -- one bit finer than [31:21], which halves the candidate bucket), the second
+// [19:9], the third [8:0].
+#define SP_SH1 20
+#define SP_SH2 9
 __device__ __forceinline__ uint32_t diff_key(float a, float b) {
   return __float_as_uint(fabsf(__fsub_rn(a, b)));   // non-negative floats order like uints
 }
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const Sparse
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (tid * EG_VEC + e >= valid) continue;
-      atomicAdd(&sh[diff_key(a.v[e], b.v[e]) >> 21], 1u);
+      atomicAdd(&sh[diff_key(a.v[e], b.v[e]) >> SP_SH1], 1u);
     }
   }
   flush(cur);
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_hist_kernel(const Sparse
     unsigned digit, above;
     block_pick(sh, SP_BINS, (unsigned)p.t_k[i], &digit, &above);
     if (tid == 0) {
-      p.sel_prefix[i] = digit;                           // top 11 bits of tau
+      p.sel_prefix[i] = digit;                           // bits [30:20] of tau
       p.sel_remain[i] = (unsigned)p.t_k[i] - above;      // rank inside that bucket
       p.cand_cnt[i] = 0u;
     }
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       keys[e] = diff_key(a.v[e], b.v[e]);
-      if (tid * EG_VEC + e < valid && (keys[e] >> 21) == prefix) {
+      if (tid * EG_VEC + e < valid && (keys[e] >> SP_SH1) == prefix) {
         m |= 1u << e;
         ++c;
       }
@@ -248,10 +253,10 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
       uint32_t* dst = p.cand + (size_t)p.tab.t_tile_start[i] * EG_TILE + s_base + woff + inc - c;
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (m & (1u << e)) *dst++ = keys[e] & 0x1FFFFFu;
+        if (m & (1u << e)) *dst++ = keys[e] & ((1u << SP_SH1) - 1u);
     }
   }
-  // ---- tensors completed by this CTA: resolve the remaining 21 bits on the candidate list alone --------------
+  // ---- tensors completed by this CTA: resolve the remaining 20 bits on the candidate list alone --------------
   const int nown = claim_completed(p.tab, p.done2, t0, t1, s_own, &s_nown);
   for (int o = 0; o < nown; ++o) {
     const int i = s_own[o];
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (cv[u] != 0xFFFFFFFFu) atomicAdd(&sh[cv[u] >> 10], 1u);
+        if (cv[u] != 0xFFFFFFFFu) atomicAdd(&sh[cv[u] >> SP_SH2], 1u);
     }
     __syncthreads();
     unsigned d2, above;
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
     remain -= above;
     // digit 3: bits [9:0] among the candidates that match digit 2
     __syncthreads();
-    for (int bkt = tid; bkt < 1024; bkt += EG_THREADS) sh[bkt] = 0u;
+    for (int bkt = tid; bkt < (1 << SP_SH2); bkt += EG_THREADS) sh[bkt] = 0u;
     __syncthreads();
     for (unsigned j0 = 0; j0 < n; j0 += 8 * EG_THREADS) {
       uint32_t cv[8];
@@ -291,13 +296,13 @@ __global__ void __launch_bounds__(EG_THREADS, 4) sparse_cand_kernel(const Sparse
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (cv[u] != 0xFFFFFFFFu && (cv[u] >> 10) == d2) atomicAdd(&sh[cv[u] & 0x3FFu], 1u);
+        if (cv[u] != 0xFFFFFFFFu && (cv[u] >> SP_SH2) == d2) atomicAdd(&sh[cv[u] & ((1u << SP_SH2) - 1u)], 1u);
     }
     __syncthreads();
     unsigned d3;
-    block_pick(sh, 1024, remain, &d3, &above);
+    block_pick(sh, 1 << SP_SH2, remain, &d3, &above);
     if (tid == 0) {
-      p.sel_prefix[i] = (p.sel_prefix[i] << 21) | (d2 << 10) | d3;    // tau: the k-th largest key, exactly
+      p.sel_prefix[i] = (p.sel_prefix[i] << SP_SH1) | (d2 << SP_SH2) | d3;    // tau: the k-th largest key, exactly
       p.sel_remain[i] = remain - above;                               // how many keys == tau are selected (>= 1)
       p.cand_cnt[i] = 0u;                                             // pass 3 reuses it as the slot counter of keys > tau
     }

@@ -137,3 +137,47 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class NvlinkCounters:
+    """Hardware NVLink byte counters of one GPU through NVML (cumulative over all links, scope id = all links):
+    DATA = payload bytes, RAW = payload + protocol overhead.  `read()` returns a dict of byte counts; take the
+    difference around a timed region to MEASURE the NVLink traffic of a kernel sequence instead of inferring it."""
+
+    def __init__(self, cuda_index: int = 0):
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.nv = pynvml
+            self.ids = {"data_tx": pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX,
+                        "data_rx": pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX,
+                        "raw_tx": pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_TX,
+                        "raw_rx": pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_RX}
+            self.ok = self.read() is not None
+        except Exception:
+            self.ok = False
+
+    def read(self):
+        try:
+            nv = self.nv
+            # scopeId UINT_MAX = aggregate over all links of the device
+            req = [(fid, 0xFFFFFFFF) for fid in self.ids.values()]
+            try:
+                vals = nv.nvmlDeviceGetFieldValues(self.h, req)
+            except Exception:
+                vals = nv.nvmlDeviceGetFieldValues(self.h, list(self.ids.values()))
+            out = {}
+            for name, v in zip(self.ids, vals):
+                if v.nvmlReturn != 0:
+                    return None
+                out[name] = int(v.value.ullVal) * 1024          # counters are in KiB
+            return out
+        except Exception:
+            return None
