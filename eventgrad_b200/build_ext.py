@@ -20,9 +20,9 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                            "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-CU_SOURCES = ["gossip.cu", "gossip_dbuf.cu", "ce_push.cu", "allreduce.cu", "allreduce_nvls.cu", "sparse.cu", "augment.cu", "ipc.cu", "bn_act.cu", "bn_nchw.cu", "linear_tc_tma.cu"]
+CU_SOURCES = ["gossip.cu", "gossip_dbuf.cu", "ce_push.cu", "allreduce.cu", "allreduce_nvls.cu", "sparse.cu", "augment.cu", "ipc.cu", "bn_act.cu", "bn_nchw.cu", "linear_tc_tma.cu", "conv_tc.cu"]
 CPP_SOURCES = ["bindings.cpp"]
-HEADERS = ["api.h", "common.cuh", "bn_common.cuh", "host_loader.h"]
+HEADERS = ["api.h", "common.cuh", "bn_common.cuh", "host_loader.h", "tc_common.cuh"]
 
 
 def so_path() -> str:

@@ -14,7 +14,7 @@ namespace egb {
 // Every launcher of this extension counts the kernels it enqueues (per family), so "how many of OUR kernels ran
 // in this region" is counted, not derived from a formula (bench.py `gpu_launches`; during CUDA-graph capture the
 // Trainer records the per-step delta and multiplies by the replays).
-enum { EG_FAM_GOSSIP = 0, EG_FAM_ALLREDUCE, EG_FAM_SPARSE, EG_FAM_BN, EG_FAM_LINEAR, EG_FAM_DATA, EG_FAM_N };
+enum { EG_FAM_GOSSIP = 0, EG_FAM_ALLREDUCE, EG_FAM_SPARSE, EG_FAM_BN, EG_FAM_LINEAR, EG_FAM_DATA, EG_FAM_CONV, EG_FAM_N };
 void eg_count_launch(int family, int n);
 
 // ------------------------------------------------------------------ tensor table (device)
@@ -253,6 +253,21 @@ struct LinearParams {
 };
 // TMA + SWIZZLE_128B + persistent CTAs (one per SM) + double-buffered TMEM accumulator
 cudaError_t launch_linear_tc_tma(const LinearParams& p, int sm_count, cudaStream_t s);
+
+// ------------------------------------------------------------------ tcgen05 3x3 convolution at fp32 accuracy
+// (csrc/conv_tc.cu): fp32 tensors split into three bf16 planes, six bf16 MMAs per fp32 product, fp32 accumulation.
+struct ConvTcParams {
+  const __nv_bfloat16* a;   // activation planes [3][N][H][W][Ca] (forward: x; dgrad: dY; wgrad: x)
+  const __nv_bfloat16* b;   // fprop/dgrad: weight planes [3][Cb][9][Ca]; wgrad: dY planes [3][N][H][W][Cb]
+  float* out;               // fprop/dgrad: [N][H][W][Cb]; wgrad: workspace [splits][9*Ca][Cb]
+  int N, H, W, Ca, Cb;
+  int bh, bn, m_tiles, k_blocks;   // filled in by the launchers
+};
+bool conv_tc_supported(int N, int H, int W, int Ca, int Cb);
+int conv_wgrad_splits(int N, int H, int W, int Ca, int Cb, int sm_count);
+cudaError_t launch_conv3x3_fprop(const ConvTcParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_conv3x3_wgrad(const ConvTcParams& p, float* dw, int splits, cudaStream_t s);
+cudaError_t launch_split3(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s);   // n % 8 == 0
 
 // ------------------------------------------------------------------ IPC window runtime
 // The RMA-window replacement (MPI_Alloc_mem + MPI_Win_create, event.cpp:138-147).

@@ -183,7 +183,7 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("launch_counts", []() {
     py::dict d;
-    const char* names[egb::EG_FAM_N] = {"gossip", "allreduce", "sparse", "bn", "linear", "data"};
+    const char* names[egb::EG_FAM_N] = {"gossip", "allreduce", "sparse", "bn", "linear", "data", "conv"};
     for (int i = 0; i < egb::EG_FAM_N; ++i) d[names[i]] = g_launches[i].load(std::memory_order_relaxed);
     return d;
   });
@@ -265,6 +265,29 @@ PYBIND11_MODULE(_C, m) {
     p.y = reinterpret_cast<void*>(y);
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.out_bf16 = out_bf16;
     check(launch_linear_tc_tma(p, sm_count, S(s)), "linear_tc");
+  });
+  m.def("conv_tc_supported", [](int N, int H, int W, int Ca, int Cb) { return conv_tc_supported(N, H, W, Ca, Cb); });
+  m.def("conv_wgrad_splits", [](int N, int H, int W, int Ca, int Cb, int sm) { return conv_wgrad_splits(N, H, W, Ca, Cb, sm); });
+  m.def("split3", [](uintptr_t src, uintptr_t dst, size_t n, uintptr_t s) {
+    check(launch_split3(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), n, S(s)), "split3");
+  });
+  m.def("conv3x3_fprop", [](uintptr_t a, uintptr_t b, uintptr_t out, int N, int H, int W, int Ca, int Cb, int sm_count,
+                            uintptr_t s) {
+    ConvTcParams p{};
+    p.a = reinterpret_cast<const __nv_bfloat16*>(a);
+    p.b = reinterpret_cast<const __nv_bfloat16*>(b);
+    p.out = reinterpret_cast<float*>(out);
+    p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb;
+    check(launch_conv3x3_fprop(p, sm_count, S(s)), "conv3x3_fprop");
+  });
+  m.def("conv3x3_wgrad", [](uintptr_t x, uintptr_t g, uintptr_t ws, uintptr_t dw, int N, int H, int W, int Ca, int Cb,
+                            int splits, uintptr_t s) {
+    ConvTcParams p{};
+    p.a = reinterpret_cast<const __nv_bfloat16*>(x);
+    p.b = reinterpret_cast<const __nv_bfloat16*>(g);
+    p.out = reinterpret_cast<float*>(ws);
+    p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb;
+    check(launch_conv3x3_wgrad(p, reinterpret_cast<float*>(dw), splits, S(s)), "conv3x3_wgrad");
   });
   m.def("decode_augment",
         [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,

@@ -20,6 +20,11 @@ class ShadowConv2d(nn.Conv2d):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.w16 is not None and x.is_cuda and torch.is_autocast_enabled():
             return self._conv_forward(x, self.w16, self.b16)
+        if (x.is_cuda and x.dtype == torch.float32 and self.bias is None and self.padding_mode == "zeros"
+                and not torch.is_autocast_enabled() and not torch.backends.cudnn.allow_tf32):
+            # reference precision (fp32): eligible 3x3 convs run on the tensor cores at fp32 accuracy (ops/conv_tc.py)
+            from .conv_tc import conv2d
+            return conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
         return super().forward(x)
 
 

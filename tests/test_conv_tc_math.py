@@ -1,0 +1,72 @@
+"""CPU checks behind csrc/conv_tc.cu: the 3 x bf16 split and the six-term product really reach fp32 accuracy, and the
+host-side tile geometry accepts exactly the shapes the kernels can tile.  (The kernels themselves are tested on a
+GPU in tests/test_gpu_conv_tc.py.)"""
+import torch
+import torch.nn.functional as F
+
+from eventgrad_b200.ops import ext
+
+
+def split3_ref(x):
+    a = x.to(torch.bfloat16).float()
+    r1 = x - a
+    b = r1.to(torch.bfloat16).float()
+    r2 = r1 - b
+    c = r2.to(torch.bfloat16).float()
+    return a, b, c
+
+
+def test_three_bf16_planes_carry_24_bits():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1 << 16, generator=g) * torch.logspace(-8, 8, 1 << 16)
+    a, b, c = split3_ref(x)
+    back = a.double() + b.double() + c.double()
+    rel = ((back - x.double()).abs() / x.double().abs()).max()
+    assert float(rel) <= 2.0 ** -23
+
+
+def test_six_term_product_is_as_accurate_as_fp32():
+    """conv as six bf16 x bf16 convolutions accumulated in fp32 (what the tensor cores compute) vs plain fp32, both
+    against fp64."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 64, 8, 8, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    truth = F.conv2d(x.double(), w.double(), padding=1)
+    xs, ws = split3_ref(x), split3_ref(w)
+    acc = torch.zeros_like(truth, dtype=torch.float32)
+    for i, j in ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0)):      # the kernel's order: small terms first
+        acc = acc + F.conv2d(xs[i], ws[j], padding=1)
+    ref32 = F.conv2d(x, w, padding=1)
+
+    def rms(a):
+        return float(((a.double() - truth) ** 2).mean().sqrt() / (truth ** 2).mean().sqrt())
+    assert rms(acc) < 2e-7
+    assert rms(acc) <= 3 * rms(ref32) + 1e-8
+    # dropping the second-order terms would NOT be fp32: bf16 x bf16 alone is ~3 decimal digits
+    assert rms(F.conv2d(xs[0], ws[0], padding=1)) > 1e-3
+
+
+def test_tile_geometry():
+    C = ext()
+    ok = [(256, 32, 32, 64, 64), (32, 32, 32, 64, 64), (256, 16, 16, 128, 128), (256, 8, 8, 256, 256),
+          (256, 4, 4, 512, 512), (5, 4, 4, 128, 64), (3, 8, 8, 64, 128), (1, 64, 64, 64, 64)]
+    bad = [(8, 32, 32, 3, 64),      # stem: 3 input channels
+           (8, 32, 32, 64, 96),     # Cout not a multiple of 64
+           (8, 28, 28, 64, 64),     # width does not divide a 128-pixel tile
+           (8, 6, 8, 64, 64)]       # 8x6 images: no whole-image tiling
+    for s in ok:
+        assert C.conv_tc_supported(*s), s
+    for s in bad:
+        assert not C.conv_tc_supported(*s), s
+    # wgrad splits: enough CTAs to fill the GPU, never more splits than 64-pixel K blocks
+    assert C.conv_wgrad_splits(256, 32, 32, 64, 64, 148) == 148 // 5
+    assert C.conv_wgrad_splits(256, 4, 4, 512, 512, 148) == 1
+    assert C.conv_wgrad_splits(1, 8, 8, 64, 64, 148) == 1
+
+
+def test_cpu_and_ineligible_shapes_fall_back_to_library_conv():
+    from eventgrad_b200.ops import conv_tc
+    x = torch.randn(2, 64, 8, 8)
+    w = torch.randn(64, 64, 3, 3)
+    assert not conv_tc.eligible(x, w, (1, 1), (1, 1), (1, 1), 1)
+    assert torch.equal(conv_tc.conv2d(x, w, None, (1, 1), (1, 1), (1, 1), 1), F.conv2d(x, w, padding=1))
