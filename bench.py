@@ -46,7 +46,10 @@ def parse():
     p.add_argument("--dtype", default="fp32", choices=["bf16", "fp32", "tf32"],
                    help="compute dtype of forward/backward. fp32 (default) = IEEE fp32 with TF32 OFF, the reference's "
                         "precision (event.cpp:279); the exchange / optimizer kernels are fp32 in every mode")
-    p.add_argument("--also", default="bf16,tf32",
+    p.add_argument("--conv-tc", default="auto", choices=["auto", "on", "off"],
+                   help="fp32 only: 3x3 convolutions on the tcgen05 tensor cores at fp32 accuracy (csrc/conv_tc.cu; "
+                        "auto = on) or cuDNN's SIMT fp32 kernels (off)")
+    p.add_argument("--also", default="fp32_cudnn,bf16,tf32",
                    help="extra dtypes measured after the headline (device-timed only) and reported under "
                         "`other_dtypes` in the same JSON line; '' to skip")
     p.add_argument("--sync-mode", default="iter", choices=["iter", "async"])
@@ -76,7 +79,11 @@ def reference_arm(args):
 
 
 def measure(args, env, dtype, want_e2e, src, sample_clocks):
-    """One Trainer at `dtype`: device-timed K steps (+ optionally the end-to-end loop).  Returns a dict."""
+    """One Trainer at `dtype`: device-timed K steps (+ optionally the end-to-end loop).  Returns a dict.
+    `fp32_cudnn` = fp32 with the tensor-core convolutions switched off (cuDNN's SIMT fp32 kernels, NCHW)."""
+    conv_tc = {"auto": None, "on": True, "off": False}[args.conv_tc]
+    if dtype == "fp32_cudnn":
+        dtype, conv_tc = "fp32", False
     import torch
     from eventgrad_b200.config import preset
     from eventgrad_b200.engine.trainer import Trainer
@@ -93,7 +100,7 @@ def measure(args, env, dtype, want_e2e, src, sample_clocks):
                  sync_mode="iter" if algo == "decent" else args.sync_mode,
                  horizon=args.horizon, topk_percent=args.topk,
                  overlap_push=tri[args.overlap] if backend == "p2p" else False,
-                 channels_last=False if args.no_channels_last else None,
+                 channels_last=False if args.no_channels_last else None, conv_tc=conv_tc,
                  cuda_graph=False if args.no_graph else None,
                  ce_push=args.ce_push, double_buffer=args.double_buffer,
                  train_samples=len(src), test_samples=256, quiet=True, augment=True)
@@ -245,6 +252,8 @@ def main():
     r = measure(args, env, args.dtype, not args.no_e2e, src, True)
     others = {}
     for dt in [d for d in args.also.split(",") if d and d != args.dtype]:
+        if dt == "fp32_cudnn" and (args.dtype != "fp32" or not r["cfg"].conv_tc):
+            continue                       # only meaningful next to a tensor-core fp32 headline
         o = measure(args, env, dt, False, src, False)
         others[dt] = {"value": o["value"], "ms_per_step": o["ms_per_step"], "loss": o["loss"],
                       "gpu_launches": o["gpu_launches"], "timing": "device-timed (CUDA events), same config otherwise"}
@@ -260,16 +269,21 @@ def main():
                    "global_batch": r["gb"], "per_gpu_batch": r["per_rank"], "seq_len": None, "image": "3x32x32",
                    "parallelism": f"dp{N}-ring-gossip" if algo != "cent" else f"dp{N}-allreduce",
                    "algorithm": args.algo, "backend": r["backend"], "sync_mode": cfg.sync_mode,
-                   "precision": {"fp32": "IEEE fp32 forward/backward, TF32 off (reference precision)",
+                   "precision": {"fp32": ("fp32 storage and fp32 accuracy, TF32 off; eligible 3x3 convolutions on the tcgen05 "
+                                          "tensor cores via 3 bf16 planes x 6 MMAs per product with fp32 round-to-nearest "
+                                          "accumulation (rms error vs fp64 1e-7, cuDNN's fp32 kernels: 2-4e-7, "
+                                          "tests/test_gpu_conv_tc.py); the other convs on cuDNN fp32"
+                                          if cfg.conv_tc else "IEEE fp32 forward/backward on cuDNN, TF32 off")
+                                         + " (reference precision)",
                                  "tf32": "TF32 tensor-core convolutions / GEMMs", "bf16": "bf16 autocast"}[args.dtype]
                                 + "; parameters, exchange, average and SGD are fp32 in every mode",
                    "overlap_push": bool(cfg.overlap_push), "double_buffer": r["dbuf"], "ce_push": bool(cfg.ce_push),
                    "nvls": r["nvls"],
                    "optimizer": "SGD lr=1e-2 momentum=0.9", "cuda_graph": bool(cfg.cuda_graph),
-                   "channels_last": bool(cfg.channels_last),
+                   "channels_last": bool(cfg.channels_last), "conv_tc": bool(cfg.conv_tc),
                    "defaults": "execution switches are the Trainer's defaults for this device (same as the CLI)"
                                if (args.overlap == "auto" and not args.no_graph and not args.no_channels_last
-                                   and not args.ce_push and args.double_buffer is None) else "overridden by flags",
+                                   and args.conv_tc == "auto" and not args.ce_push and args.double_buffer is None) else "overridden by flags",
                    "l2_policy": "per-step working set (theta,grad,mom,2 inboxes = "
                                 f"{5 * table.n_padded * 4 / 1e6:.0f} MB + activations) exceeds the 126 MB L2; "
                                 "no explicit flush"},

@@ -72,7 +72,9 @@ class TrainConfig:
     # ---- execution ---------------------------------------------------------
     device: str = "auto"             # auto | cuda | cpu
     dtype: str = "fp32"              # fp32 | tf32 | bf16 (compute dtype; arena is fp32)
-    channels_last: Optional[bool] = None   # None = auto on CUDA: NHWC for bf16/tf32, NCHW for fp32 (fused BN kernels in both)
+    channels_last: Optional[bool] = None   # None = auto on CUDA: NHWC, except fp32 with conv_tc off (cuDNN's fp32 convs are NCHW)
+    conv_tc: Optional[bool] = None         # fp32 only: 3x3 convs on the tcgen05 tensor cores at fp32 accuracy (csrc/conv_tc.cu);
+                                           # None = on for CUDA (EGB_CONV_TC=0 turns it off); False = cuDNN's SIMT fp32 kernels
     cuda_graph: Optional[bool] = None      # None = auto: whole-step CUDA graph on CUDA
     max_steps: int = 0               # >0: stop after this many steps (tests / bench)
     cudnn_benchmark: bool = True     # cuDNN autotune: best steady state, but every new conv shape costs a
@@ -112,11 +114,15 @@ class TrainConfig:
         cuda = device_type == "cuda"
         p2p = self.backend == "p2p" or (self.backend == "auto" and cuda)
         kw = {}
+        conv_tc = self.conv_tc
+        if conv_tc is None:
+            import os
+            conv_tc = kw["conv_tc"] = bool(cuda and self.dtype == "fp32" and os.environ.get("EGB_CONV_TC", "1") != "0")
         if self.channels_last is None:
-            # bf16 / tf32: NHWC (tensor-core convolutions want it).  fp32: cuDNN's IEEE-fp32 convolutions are NCHW
-            # kernels -- fed NHWC they transpose around every conv (measured 36.9 vs 27.8 ms/step on B200), so the
-            # reference-precision path stays NCHW; the fused BN kernels exist for both layouts
-            kw["channels_last"] = cuda and self.dtype != "fp32"
+            # bf16 / tf32 / fp32 on our tensor-core convolutions: NHWC.  fp32 on cuDNN (conv_tc off): its IEEE-fp32
+            # convolutions are NCHW kernels -- fed NHWC they transpose around every conv (measured 36.9 vs 27.8 ms/step
+            # on B200) -- so that path stays NCHW; the fused BN kernels exist for both layouts
+            kw["channels_last"] = cuda and (self.dtype != "fp32" or conv_tc)
         if self.cuda_graph is None:
             kw["cuda_graph"] = cuda
         if self.overlap_push is None:

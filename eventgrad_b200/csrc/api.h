@@ -254,20 +254,28 @@ struct LinearParams {
 // TMA + SWIZZLE_128B + persistent CTAs (one per SM) + double-buffered TMEM accumulator
 cudaError_t launch_linear_tc_tma(const LinearParams& p, int sm_count, cudaStream_t s);
 
-// ------------------------------------------------------------------ tcgen05 3x3 convolution at fp32 accuracy
+// ------------------------------------------------------------------ tcgen05 convolutions at fp32 accuracy
 // (csrc/conv_tc.cu): fp32 tensors split into three bf16 planes, six bf16 MMAs per fp32 product, fp32 accumulation.
+// One kernel pair + a tap table covers 3x3 stride 1/2, 1x1 stride 2 and the 3-channel stem (see conv_tc.cu).
 struct ConvTcParams {
-  const __nv_bfloat16* a;   // activation planes [3][N][H][W][Ca] (forward: x; dgrad: dY; wgrad: x)
-  const __nv_bfloat16* b;   // fprop/dgrad: weight planes [3][Cb][9][Ca]; wgrad: dY planes [3][N][H][W][Cb]
-  float* out;               // fprop/dgrad: [N][H][W][Cb]; wgrad: workspace [splits][9*Ca][Cb]
-  int N, H, W, Ca, Cb;
+  const __nv_bfloat16* a;   // activation planes [3][nsrc][N][H][W][Ca] (forward: x; dgrad: dY; wgrad: x)
+  const __nv_bfloat16* b;   // fprop/dgrad: weight planes [3][Cb][wtaps*Ca]; wgrad: dY planes [3][N][H][W][Cb]
+  float* out;               // fprop/dgrad: [N][OH][OW][Cb]; wgrad: workspace [splits][ntaps*Ca][Cb]
+  int N, H, W;              // pixel grid of the GEMM rows
+  int Ca, Cb;
+  int ntaps, nsrc, wtaps;   // taps of this launch, source sub-images per plane, taps in the weight matrix
+  signed char dh[9], dw[9], src[9], wk[9];
+  int OH, OW, os, op, oq;   // fprop: pixel (n,i,j) -> out[n][i*os+op][j*os+oq]
   int bh, bn, m_tiles, k_blocks;   // filled in by the launchers
 };
 bool conv_tc_supported(int N, int H, int W, int Ca, int Cb);
-int conv_wgrad_splits(int N, int H, int W, int Ca, int Cb, int sm_count);
-cudaError_t launch_conv3x3_fprop(const ConvTcParams& p, int sm_count, cudaStream_t s);
-cudaError_t launch_conv3x3_wgrad(const ConvTcParams& p, float* dw, int splits, cudaStream_t s);
+int conv_wgrad_splits(int N, int H, int W, int Ca, int Cb, int ntaps, int sm_count);
+cudaError_t launch_conv_fprop(const ConvTcParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_conv_wgrad(const ConvTcParams& p, float* dw, int splits, cudaStream_t s);
 cudaError_t launch_split3(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s);   // n % 8 == 0
+cudaError_t launch_split3_parity(const float* src, __nv_bfloat16* dst, int N, int H, int W, int C, cudaStream_t s);
+cudaError_t launch_split3_stem(const float* src, __nv_bfloat16* dst, int N, int H, int W, cudaStream_t s);
+cudaError_t launch_conv_wprep(const float* w, __nv_bfloat16* wp, __nv_bfloat16* wtp, int Co, int T, int Ci, cudaStream_t s);
 
 // ------------------------------------------------------------------ IPC window runtime
 // The RMA-window replacement (MPI_Alloc_mem + MPI_Win_create, event.cpp:138-147).

@@ -8,6 +8,8 @@
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <tuple>
+#include <vector>
 #include <unordered_map>
 
 #include "api.h"
@@ -267,27 +269,57 @@ PYBIND11_MODULE(_C, m) {
     check(launch_linear_tc_tma(p, sm_count, S(s)), "linear_tc");
   });
   m.def("conv_tc_supported", [](int N, int H, int W, int Ca, int Cb) { return conv_tc_supported(N, H, W, Ca, Cb); });
-  m.def("conv_wgrad_splits", [](int N, int H, int W, int Ca, int Cb, int sm) { return conv_wgrad_splits(N, H, W, Ca, Cb, sm); });
+  m.def("conv_wgrad_splits", [](int N, int H, int W, int Ca, int Cb, int ntaps, int sm) {
+    return conv_wgrad_splits(N, H, W, Ca, Cb, ntaps, sm);
+  });
   m.def("split3", [](uintptr_t src, uintptr_t dst, size_t n, uintptr_t s) {
     check(launch_split3(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), n, S(s)), "split3");
   });
-  m.def("conv3x3_fprop", [](uintptr_t a, uintptr_t b, uintptr_t out, int N, int H, int W, int Ca, int Cb, int sm_count,
-                            uintptr_t s) {
+  m.def("split3_parity", [](uintptr_t src, uintptr_t dst, int N, int H, int W, int C, uintptr_t s) {
+    check(launch_split3_parity(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), N, H, W, C, S(s)),
+          "split3_parity");
+  });
+  m.def("split3_stem", [](uintptr_t src, uintptr_t dst, int N, int H, int W, uintptr_t s) {
+    check(launch_split3_stem(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), N, H, W, S(s)),
+          "split3_stem");
+  });
+  m.def("conv_wprep", [](uintptr_t w, uintptr_t wp, uintptr_t wtp, int Co, int T, int Ci, uintptr_t s) {
+    check(launch_conv_wprep(reinterpret_cast<const float*>(w), reinterpret_cast<__nv_bfloat16*>(wp),
+                            reinterpret_cast<__nv_bfloat16*>(wtp), Co, T, Ci, S(s)), "conv_wprep");
+  });
+  // taps: list of (dh, dw, src, wk)
+  auto fill = [](ConvTcParams& p, const std::vector<std::tuple<int, int, int, int>>& taps) {
+    if (taps.empty() || taps.size() > 9) throw std::invalid_argument("1..9 taps");
+    p.ntaps = (int)taps.size();
+    for (int t = 0; t < p.ntaps; ++t) {
+      p.dh[t] = (signed char)std::get<0>(taps[t]);
+      p.dw[t] = (signed char)std::get<1>(taps[t]);
+      p.src[t] = (signed char)std::get<2>(taps[t]);
+      p.wk[t] = (signed char)std::get<3>(taps[t]);
+    }
+  };
+  m.def("conv_fprop", [fill](uintptr_t a, uintptr_t b, uintptr_t out, int N, int H, int W, int Ca, int Cb,
+                             std::vector<std::tuple<int, int, int, int>> taps, int nsrc, int wtaps, int OH, int OW, int os,
+                             int op, int oq, int sm_count, uintptr_t s) {
     ConvTcParams p{};
     p.a = reinterpret_cast<const __nv_bfloat16*>(a);
     p.b = reinterpret_cast<const __nv_bfloat16*>(b);
     p.out = reinterpret_cast<float*>(out);
-    p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb;
-    check(launch_conv3x3_fprop(p, sm_count, S(s)), "conv3x3_fprop");
+    p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb; p.nsrc = nsrc; p.wtaps = wtaps;
+    p.OH = OH; p.OW = OW; p.os = os; p.op = op; p.oq = oq;
+    fill(p, taps);
+    check(launch_conv_fprop(p, sm_count, S(s)), "conv_fprop");
   });
-  m.def("conv3x3_wgrad", [](uintptr_t x, uintptr_t g, uintptr_t ws, uintptr_t dw, int N, int H, int W, int Ca, int Cb,
-                            int splits, uintptr_t s) {
+  m.def("conv_wgrad", [fill](uintptr_t x, uintptr_t g, uintptr_t ws, uintptr_t dw, int N, int H, int W, int Ca, int Cb,
+                             std::vector<std::tuple<int, int, int, int>> taps, int nsrc, int splits, uintptr_t s) {
     ConvTcParams p{};
     p.a = reinterpret_cast<const __nv_bfloat16*>(x);
     p.b = reinterpret_cast<const __nv_bfloat16*>(g);
     p.out = reinterpret_cast<float*>(ws);
-    p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb;
-    check(launch_conv3x3_wgrad(p, reinterpret_cast<float*>(dw), splits, S(s)), "conv3x3_wgrad");
+    p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb; p.nsrc = nsrc; p.wtaps = (int)taps.size();
+    p.OH = H; p.OW = W; p.os = 1;
+    fill(p, taps);
+    check(launch_conv_wgrad(p, reinterpret_cast<float*>(dw), splits, S(s)), "conv_wgrad");
   });
   m.def("decode_augment",
         [](uintptr_t in, uintptr_t out, uintptr_t oy, uintptr_t ox, uintptr_t flip, int B, int C, int H, int W,

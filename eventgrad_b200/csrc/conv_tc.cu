@@ -24,7 +24,18 @@
 //       both operands are "MN-major" (the contiguous dimension is the channel, K = pixels), expressed with MN-major
 //       SWIZZLE_128B descriptors over the very same TMA boxes; split over pixel ranges, partial sums in a workspace,
 //   conv_wgrad_reduce_kernel   fixed-order (deterministic) sum of the partials + transpose to the OHWI weight layout.
-//   split3_kernel          fp32 -> three bf16 planes.
+//   split3_kernel          fp32 -> three bf16 planes (flat; "parity" variant: the four (h%2, w%2) sub-images of the
+//                          input of a STRIDE-2 conv, so that its taps become unit-stride boxes; "stem" variant: the 27
+//                          (tap, rgb) values of the 3-channel stem gathered into one 64-wide K block = a 1x1 conv)
+//   conv_wprep_kernel      weights fp32 [Co][T][Ci] -> planes [3][Co][T*Ci] (forward) and [3][Ci][T*Co] (data gradient).
+//
+// One kernel pair serves every convolution of the network through a TAP TABLE (ConvTcParams.dh/dw/src/wk): tap t
+// reads source sub-image src[t] shifted by (dh[t], dw[t]) and the weight slice wk[t]:
+//   3x3 stride 1      9 taps, shift (r-1, s-1)                      dgrad: same taps, weight slice 8-t of W^T
+//   3x3 stride 2      9 taps over the parity images, shift in {-1,0}   dgrad: 4 launches, one per INPUT parity class
+//                                                                   (1/2/2/4 taps over dY, scattered with stride 2)
+//   1x1 stride 2      1 tap over parity image (0,0)                 dgrad: class (0,0) only, the rest is zero
+//   stem (3 -> 64)    1 tap over the gathered 64-wide patches       (no data gradient: the input is the image)
 #include "api.h"
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -55,7 +66,7 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   constexpr uint32_t NCOLS = 2u * NT;                      // two accumulators (128 or 256 columns: powers of two)
-  const int cpb = p.Ca / 64, num_kb = 9 * cpb;
+  const int cpb = p.Ca / 64, num_kb = p.ntaps * cpb;
   const int n_tiles = p.Cb / NT;
   const int total = p.m_tiles * n_tiles;
   const int tpi = p.bn == 1 ? p.H / p.bh : 1;              // tiles per image
@@ -88,16 +99,16 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           const int tap = kb / cpb, cc = kb - tap * cpb;
-          const int r = tap / 3, sx = tap - r * 3;
+          const int dh = p.dh[tap], dw = p.dw[tap], src = p.src[tap], wk = p.wk[tap];
           bar_wait(empty0 + 8u * s, ph ^ 1u);
           bar_expect_tx(full0 + 8u * s, STAGE);
           const uint32_t sa = smem0 + s * STAGE;
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl)      // shifted window; rows outside the image arrive as zeros (= padding)
-            tma_load_5d(sa + pl * CV_APLANE, &tmA, full0 + 8u * s, cc * 64, sx - 1, h0 + r - 1, n0, pl);
+            tma_load_5d(sa + pl * CV_APLANE, &tmA, full0 + 8u * s, cc * 64, dw, h0 + dh, n0, pl * p.nsrc + src);
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl)
-            tma_load_2d(sa + A_BYTES + pl * B_PLANE, &tmB, full0 + 8u * s, tap * p.Ca + cc * 64, pl * p.Cb + nt * NT);
+            tma_load_2d(sa + A_BYTES + pl * B_PLANE, &tmB, full0 + 8u * s, wk * p.Ca + cc * 64, pl * p.Cb + nt * NT);
         }
       }
     }
@@ -160,7 +171,14 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       const long long row = (long long)mt * 128 + q * 32 + lane;
       if (row < M) {
-        float4* dst = reinterpret_cast<float4*>(p.out + (size_t)row * p.Cb + nt * NT);
+        long long opix = row;
+        if (p.os != 1 || p.OH != p.H || p.OW != p.W) {          // strided scatter (data gradient of a stride-2 conv)
+          const int hw = p.H * p.W;
+          const int n = (int)(row / hw), rem = (int)(row - (long long)n * hw);
+          const int i = rem / p.W, j = rem - i * p.W;
+          opix = ((long long)n * p.OH + i * p.os + p.op) * p.OW + j * p.os + p.oq;
+        }
+        float4* dst = reinterpret_cast<float4*>(p.out + (size_t)opix * p.Cb + nt * NT);
 #pragma unroll
         for (int j = 0; j < NT / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
@@ -172,7 +190,7 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-// grid (ceil(U/2), Cb/NT, splits); U = 9 * Ca/64 "units" (tap, 64-channel block of the input); one CTA accumulates
+// grid (ceil(U/2), Cb/NT, splits); U = ntaps * Ca/64 "units" (tap, 64-channel block of the input); one CTA accumulates
 // D[128 = two units][NT] over its range of 64-pixel K blocks and writes the partial to ws[split][unit*64 + ci][co].
 template <int NT, int STAGES>
 __global__ void __launch_bounds__(CV_THREADS, 1)
@@ -190,7 +208,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   constexpr uint32_t NCOLS = 2u * NT;
-  const int cpb = p.Ca / 64, U = 9 * cpb;
+  const int cpb = p.Ca / 64, U = p.ntaps * cpb;
   const int u0 = 2 * blockIdx.x, u1 = (u0 + 1 < U) ? u0 + 1 : u0;
   const int per = (p.k_blocks + (int)gridDim.z - 1) / (int)gridDim.z;
   const int kb0 = blockIdx.z * per, kb1 = min(p.k_blocks, kb0 + per);
@@ -231,8 +249,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
-            const int r = tap[blk] / 3, sx = tap[blk] - r * 3;
-            tma_load_5d(sa + pl * CV_APLANE + blk * BLK, &tmX, full0 + 8u * s, cb64[blk] * 64, sx - 1, h0 + r - 1, n0, pl);
+            const int t = tap[blk];
+            tma_load_5d(sa + pl * CV_APLANE + blk * BLK, &tmX, full0 + 8u * s, cb64[blk] * 64, p.dw[t], h0 + p.dh[t], n0,
+                        pl * p.nsrc + p.src[t]);
           }
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl)
@@ -291,7 +310,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     if (store) {
       float4* dst = reinterpret_cast<float4*>(
-          p.out + ((size_t)blockIdx.z * (9 * p.Ca) + (size_t)unit * 64 + (m & 63)) * p.Cb + blockIdx.y * NT);
+          p.out + ((size_t)blockIdx.z * (p.ntaps * p.Ca) + (size_t)unit * 64 + (m & 63)) * p.Cb + blockIdx.y * NT);
 #pragma unroll
       for (int j = 0; j < NT / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
@@ -348,11 +367,103 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ s
   }
 }
 
+// Input of a stride-2 conv: x [N][H][W][C] fp32 -> planes [3][4][N][H/2][W/2][C]; sub-image (h%2)*2 + (w%2) holds the
+// pixels of that parity, so tap (r,s) of the strided conv is a UNIT-stride box of one sub-image shifted by -1 or 0.
+__global__ void __launch_bounds__(256) split3_parity_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            int N, int H, int W, int C) {
+  const int c8 = C / 8;
+  const size_t n8 = (size_t)N * H * W * c8, plane = (size_t)N * H * W * C;
+  const int H2 = H / 2, W2 = W / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / c8;
+    const int cg = (int)(i - pix * c8);
+    const int w = (int)(pix % W);
+    const size_t t = pix / W;
+    const int h = (int)(t % H), n = (int)(t / H);
+    const int sub = (h & 1) * 2 + (w & 1);
+    const size_t o = ((((size_t)sub * N + n) * H2 + (h >> 1)) * W2 + (w >> 1)) * C + (size_t)cg * 8;
+    const F8 x = ld_f8(src + i * 8);
+    __nv_bfloat16 a[8], b[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3(x.v[j], a[j], b[j], c[j]);
+    *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(a);
+    *reinterpret_cast<uint4*>(dst + plane + o) = *reinterpret_cast<const uint4*>(b);
+    *reinterpret_cast<uint4*>(dst + 2 * plane + o) = *reinterpret_cast<const uint4*>(c);
+  }
+}
+
+// Stem (Cin = 3): gather the 27 values (tap, rgb) of every output pixel's 3x3 window into ONE 64-wide K block
+// (k = (r*3+s)*3 + c, zero beyond 27 and outside the image): the stem becomes a 1x1 convolution with K = 64.
+// x [N][H][W][3] fp32 -> planes [3][N][H][W][64].
+__global__ void __launch_bounds__(256) split3_stem_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          int N, int H, int W) {
+  const size_t n8 = (size_t)N * H * W * 8, plane = (size_t)N * H * W * 64;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i >> 3;
+    const int g = (int)(i & 7);
+    const int w = (int)(pix % W);
+    const size_t t = pix / W;
+    const int h = (int)(t % H), n = (int)(t / H);
+    __nv_bfloat16 a[8], b[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < 27) {
+        const int tap = k / 3, ch = k - tap * 3;
+        const int r = tap / 3, sx = tap - r * 3;
+        const int hh = h + r - 1, ww = w + sx - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(src + (((size_t)n * H + hh) * W + ww) * 3 + ch);
+      }
+      split3(v, a[j], b[j], c[j]);
+    }
+    *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(a);
+    *reinterpret_cast<uint4*>(dst + plane + i * 8) = *reinterpret_cast<const uint4*>(b);
+    *reinterpret_cast<uint4*>(dst + 2 * plane + i * 8) = *reinterpret_cast<const uint4*>(c);
+  }
+}
+
+// Weights, once per step: w fp32 [Co][T][Ci] (OHWI) -> wp planes [3][Co][T*Ci] (same order: the forward's B operand)
+// and, when wtp != null, wtp planes [3][Ci][T*Co] (wt[ci][t][co] = w[co][t][ci]: the data gradient's B operand).
+// grid (Ci/32, Co/32, T), 256 threads (32 x 8).
+__global__ void __launch_bounds__(256) conv_wprep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                         __nv_bfloat16* __restrict__ wtp, int Co, int T, int Ci) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, t = blockIdx.z;
+  const size_t plane = (size_t)Co * T * Ci;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty + 8 * i;
+    const size_t idx = ((size_t)co * T + t) * Ci + ci0 + tx;
+    const float v = __ldg(w + idx);
+    tile[ty + 8 * i][tx] = v;
+    __nv_bfloat16 a, b, c;
+    split3(v, a, b, c);
+    wp[idx] = a;
+    wp[plane + idx] = b;
+    wp[2 * plane + idx] = c;
+  }
+  if (wtp == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty + 8 * i;
+    const size_t idx = ((size_t)ci * T + t) * Co + co0 + tx;
+    __nv_bfloat16 a, b, c;
+    split3(tile[tx][ty + 8 * i], a, b, c);
+    wtp[idx] = a;
+    wtp[plane + idx] = b;
+    wtp[2 * plane + idx] = c;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
-static bool make_map_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int box_w, int box_h, int box_n) {
+static bool make_map_act(CUtensorMap* m, const void* base, int C, int W, int H, int N, int planes, int box_w, int box_h,
+                         int box_n) {
   EgEncodeTiledFn enc = eg_get_encode_tiled();
   if (enc == nullptr) return false;
-  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 3};
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)planes};
   const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                                  (cuuint64_t)N * H * W * C * 2};
   const cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n, 1};
@@ -388,22 +499,30 @@ static bool tile_geometry(int N, int H, int W, int rows, int* bh, int* bn, int* 
   return true;
 }
 
+// (N, H, W) = the pixel grid of the GEMM rows (the conv's OUTPUT grid; dY's grid for a stride-2 data gradient)
 bool conv_tc_supported(int N, int H, int W, int Ca, int Cb) {
   int bh, bn, t;
   return N >= 1 && Ca % 64 == 0 && Cb % 64 == 0 && Ca >= 64 && Cb >= 64 && tile_geometry(N, H, W, 128, &bh, &bn, &t) &&
          tile_geometry(N, H, W, 64, &bh, &bn, &t);
 }
 
-int conv_wgrad_splits(int N, int H, int W, int Ca, int Cb, int sm_count) {
+int conv_wgrad_splits(int N, int H, int W, int Ca, int Cb, int ntaps, int sm_count) {
   int bh, bn, kblocks;
   if (!tile_geometry(N, H, W, 64, &bh, &bn, &kblocks)) return 0;
   const int NT = (Cb % 128 == 0) ? 128 : 64;
-  const int U = 9 * (Ca / 64);
+  const int U = ntaps * (Ca / 64);
   const int work = ((U + 1) / 2) * (Cb / NT);
   int s = sm_count / work;
   if (s < 1) s = 1;
   if (s > kblocks) s = kblocks;
   return s;
+}
+
+static bool taps_ok(const ConvTcParams& p) {
+  if (p.ntaps < 1 || p.ntaps > 9 || p.nsrc < 1 || p.nsrc > 4 || p.wtaps < 1 || p.wtaps > 9) return false;
+  for (int t = 0; t < p.ntaps; ++t)
+    if (p.src[t] < 0 || p.src[t] >= p.nsrc || p.wk[t] < 0 || p.wk[t] >= p.wtaps) return false;
+  return true;
 }
 
 template <int NT, int STAGES>
@@ -416,14 +535,17 @@ static cudaError_t fprop_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv3x3_fprop(const ConvTcParams& p0, int sm_count, cudaStream_t s) {
+// p.a = activation planes [3][nsrc][N][H][W][Ca], p.b = weight planes [3][Cb][wtaps*Ca], p.out fp32 [N][OH][OW][Cb]
+cudaError_t launch_conv_fprop(const ConvTcParams& p0, int sm_count, cudaStream_t s) {
   ConvTcParams p = p0;
-  if (!conv_tc_supported(p.N, p.H, p.W, p.Ca, p.Cb)) return cudaErrorInvalidValue;
+  if (!conv_tc_supported(p.N, p.H, p.W, p.Ca, p.Cb) || !taps_ok(p)) return cudaErrorInvalidValue;
+  if (p.os < 1 || p.op < 0 || p.oq < 0 || p.op >= p.os || p.oq >= p.os || p.OH < p.H * p.os || p.OW < p.W * p.os)
+    return cudaErrorInvalidValue;
   tile_geometry(p.N, p.H, p.W, 128, &p.bh, &p.bn, &p.m_tiles);
   CUtensorMap tmA, tmB;
   const int NT = (p.Cb % 128 == 0) ? 128 : 64;
-  if (!make_map_act(&tmA, p.a, p.Ca, p.W, p.H, p.N, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
-  if (!make_map_w(&tmB, p.b, (uint64_t)9 * p.Ca, (uint64_t)3 * p.Cb, (uint32_t)NT)) return cudaErrorNotSupported;
+  if (!make_map_act(&tmA, p.a, p.Ca, p.W, p.H, p.N, 3 * p.nsrc, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
+  if (!make_map_w(&tmB, p.b, (uint64_t)p.wtaps * p.Ca, (uint64_t)3 * p.Cb, (uint32_t)NT)) return cudaErrorNotSupported;
   const int total = p.m_tiles * (p.Cb / NT);
   const int grid = total < sm_count ? total : sm_count;
   eg_count_launch(EG_FAM_CONV, 1);
@@ -440,35 +562,58 @@ static cudaError_t wgrad_launch(const CUtensorMap& tmX, const CUtensorMap& tmG, 
   return cudaGetLastError();
 }
 
-// p.a = input planes [3][N][H][W][Ca], p.b = dY planes [3][N][H][W][Cb], p.out = workspace [splits][9*Ca][Cb],
-// dw = [Cb][9][Ca] (OHWI)
-cudaError_t launch_conv3x3_wgrad(const ConvTcParams& p0, float* dw, int splits, cudaStream_t s) {
+// p.a = input planes [3][nsrc][N][H][W][Ca], p.b = dY planes [3][N][H][W][Cb], p.out = workspace
+// [splits][ntaps*Ca][Cb], dw = [Cb][ntaps][Ca] (OHWI)
+cudaError_t launch_conv_wgrad(const ConvTcParams& p0, float* dw, int splits, cudaStream_t s) {
   ConvTcParams p = p0;
-  if (!conv_tc_supported(p.N, p.H, p.W, p.Ca, p.Cb) || splits < 1) return cudaErrorInvalidValue;
+  if (!conv_tc_supported(p.N, p.H, p.W, p.Ca, p.Cb) || !taps_ok(p) || splits < 1) return cudaErrorInvalidValue;
   tile_geometry(p.N, p.H, p.W, 64, &p.bh, &p.bn, &p.k_blocks);
   if (splits > p.k_blocks) splits = p.k_blocks;
   CUtensorMap tmX, tmG;
   const int NT = (p.Cb % 128 == 0) ? 128 : 64;
-  if (!make_map_act(&tmX, p.a, p.Ca, p.W, p.H, p.N, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
-  if (!make_map_act(&tmG, p.b, p.Cb, p.W, p.H, p.N, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
-  const int U = 9 * (p.Ca / 64);
+  if (!make_map_act(&tmX, p.a, p.Ca, p.W, p.H, p.N, 3 * p.nsrc, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
+  if (!make_map_act(&tmG, p.b, p.Cb, p.W, p.H, p.N, 3, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
+  const int U = p.ntaps * (p.Ca / 64);
   const dim3 grid((U + 1) / 2, p.Cb / NT, splits);
   eg_count_launch(EG_FAM_CONV, 2);
   cudaError_t e = NT == 128 ? wgrad_launch<128, 2>(tmX, tmG, p, grid, s) : wgrad_launch<64, 3>(tmX, tmG, p, grid, s);
   if (e != cudaSuccess) return e;
-  const int rows = 9 * p.Ca;
+  const int rows = p.ntaps * p.Ca;
   conv_wgrad_reduce_kernel<<<dim3((rows + 31) / 32, p.Cb / 32), 256, 0, s>>>(p.out, dw, rows, p.Cb, splits);
   return cudaGetLastError();
 }
 
-cudaError_t launch_split3(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
-  if (n % 8) return cudaErrorInvalidValue;
-  const size_t n8 = n / 8;
+static unsigned split_blocks(size_t n8) {
   size_t blocks = (n8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+cudaError_t launch_split3(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
+  if (n % 8) return cudaErrorInvalidValue;
   eg_count_launch(EG_FAM_CONV, 1);
-  split3_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, n8, n);
+  split3_kernel<<<split_blocks(n / 8), 256, 0, s>>>(src, dst, n / 8, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split3_parity(const float* src, __nv_bfloat16* dst, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) return cudaErrorInvalidValue;
+  eg_count_launch(EG_FAM_CONV, 1);
+  split3_parity_kernel<<<split_blocks((size_t)N * H * W * C / 8), 256, 0, s>>>(src, dst, N, H, W, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split3_stem(const float* src, __nv_bfloat16* dst, int N, int H, int W, cudaStream_t s) {
+  eg_count_launch(EG_FAM_CONV, 1);
+  split3_stem_kernel<<<split_blocks((size_t)N * H * W * 8), 256, 0, s>>>(src, dst, N, H, W);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_wprep(const float* w, __nv_bfloat16* wp, __nv_bfloat16* wtp, int Co, int T, int Ci, cudaStream_t s) {
+  if (Co % 32 || Ci % 32 || T < 1) return cudaErrorInvalidValue;
+  eg_count_launch(EG_FAM_CONV, 1);
+  conv_wprep_kernel<<<dim3(Ci / 32, Co / 32, T), 256, 0, s>>>(w, wp, wtp, Co, T, Ci);
   return cudaGetLastError();
 }
 

@@ -49,6 +49,8 @@ class Trainer:
             tf32 = cfg.dtype == "tf32"
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.backends.cudnn.allow_tf32 = tf32
+            from ..ops import conv_tc as _conv_tc
+            _conv_tc.set_enabled(bool(cfg.conv_tc))       # fp32: eligible 3x3 convs on tcgen05 at fp32 accuracy
         if dev.type == "cuda":
             torch.backends.cudnn.benchmark = bool(cfg.cudnn_benchmark)
             if cfg.host_threads > 0:

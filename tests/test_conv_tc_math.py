@@ -59,9 +59,65 @@ def test_tile_geometry():
     for s in bad:
         assert not C.conv_tc_supported(*s), s
     # wgrad splits: enough CTAs to fill the GPU, never more splits than 64-pixel K blocks
-    assert C.conv_wgrad_splits(256, 32, 32, 64, 64, 148) == 148 // 5
-    assert C.conv_wgrad_splits(256, 4, 4, 512, 512, 148) == 1
-    assert C.conv_wgrad_splits(1, 8, 8, 64, 64, 148) == 1
+    assert C.conv_wgrad_splits(256, 32, 32, 64, 64, 9, 148) == 148 // 5
+    assert C.conv_wgrad_splits(256, 4, 4, 512, 512, 9, 148) == 1
+    assert C.conv_wgrad_splits(1, 8, 8, 64, 64, 9, 148) == 1
+    assert C.conv_wgrad_splits(256, 32, 32, 64, 64, 1, 148) == 148      # stem / 1x1: one unit pair
+
+
+def test_tap_tables():
+    """the tap tables of ops/conv_tc.py against the definition of the strided convolution and its transpose"""
+    from eventgrad_b200.ops import conv_tc as ct
+    # forward stride 2 / pad 1: output row ho reads input row 2*ho + r - 1 = 2*(ho + dh) + parity
+    for (dh, dw, src, wk) in ct.TAPS_S2:
+        r, s = divmod(wk, 3)
+        ph, pw = divmod(src, 2)
+        assert 2 * dh + ph == r - 1 and 2 * dw + pw == s - 1
+    # data gradient: input row 2*i + p receives from output row i + a through filter row r  <=>  2*(i+a) + r - 1 == 2*i + p
+    seen = set()
+    for (p, q), taps in ct.TAPS_S2_DGRAD.items():
+        for (a, b, src, wk) in taps:
+            r, s = divmod(wk, 3)
+            assert src == 0 and 2 * a + r - 1 == p and 2 * b + s - 1 == q
+            seen.add(wk)
+    assert seen == set(range(9)) and sum(len(t) for t in ct.TAPS_S2_DGRAD.values()) == 9
+    assert [t[3] for t in ct.TAPS_S1_DGRAD] == list(range(8, -1, -1))
+
+
+def test_s2_dgrad_by_parity_classes_matches_autograd():
+    """emulate the four-launch data gradient of the stride-2 conv with plain tensor ops"""
+    from eventgrad_b200.ops import conv_tc as ct
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(5, 4, 3, 3, generator=g, dtype=torch.float64)
+    dy = torch.randn(2, 5, 4, 4, generator=g, dtype=torch.float64)
+    F.conv2d(x, w, stride=2, padding=1).backward(dy)
+    dx = torch.zeros(2, 4, 8, 8, dtype=torch.float64)
+    dyp = F.pad(dy, (1, 1, 1, 1))                      # zero outside, like the TMA fill
+    for (p, q), taps in ct.TAPS_S2_DGRAD.items():
+        acc = torch.zeros(2, 4, 4, 4, dtype=torch.float64)
+        for (a, b, _, wk) in taps:
+            r, s = divmod(wk, 3)
+            win = dyp[:, :, 1 + a:5 + a, 1 + b:5 + b]                  # dY[i + a, j + b]
+            acc += torch.einsum("nohw,oc->nchw", win, w[:, :, r, s])
+        dx[:, :, p::2, q::2] = acc
+    assert torch.allclose(dx, x.grad, atol=1e-12)
+
+
+def test_s2_forward_by_parity_images_matches_conv():
+    from eventgrad_b200.ops import conv_tc as ct
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 4, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, stride=2, padding=1)
+    y = torch.zeros_like(ref)
+    for (dh, dw, src, wk) in ct.TAPS_S2:
+        r, s = divmod(wk, 3)
+        ph, pw = divmod(src, 2)
+        sub = F.pad(x[:, :, ph::2, pw::2], (1, 1, 1, 1))               # parity image, zero outside
+        win = sub[:, :, 1 + dh:5 + dh, 1 + dw:5 + dw]
+        y += torch.einsum("nchw,oc->nohw", win, w[:, :, r, s])
+    assert torch.allclose(y, ref, atol=1e-12)
 
 
 def test_cpu_and_ineligible_shapes_fall_back_to_library_conv():

@@ -94,6 +94,50 @@ def test_backward_matches_fp64(N, H, W, Ca, Cb):
     assert w1.grad.stride() == w1.stride()
 
 
+KINDS = [  # kind, N, H, W, Cin, Cout, kernel, stride, pad
+    ("s2", 4, 32, 32, 64, 128, 3, 2, 1),
+    ("s2", 4, 16, 16, 128, 256, 3, 2, 1),
+    ("s2", 9, 8, 8, 256, 512, 3, 2, 1),       # 4x4 outputs, 9 images: zero-filled tail of the 8-image tile
+    ("p2", 4, 32, 32, 64, 128, 1, 2, 0),
+    ("p2", 8, 8, 8, 256, 512, 1, 2, 0),
+    ("p1", 4, 16, 16, 64, 256, 1, 1, 0),
+    ("stem", 8, 32, 32, 3, 64, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("kind,N,H,W,Ci,Co,k,st,pd", KINDS)
+def test_strided_pointwise_and_stem_match_fp64(kind, N, H, W, Ci, Co, k, st, pd):
+    """the other members of the tap-table family: forward, data gradient and weight gradient against fp64"""
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, Ci, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Co, Ci, k, k, device="cuda", generator=g) * (2.0 / (k * k * Ci)) ** 0.5).contiguous(
+        memory_format=torch.channels_last)
+    assert conv_tc.kind_of(x, w, (st, st), (pd, pd), (1, 1), 1) == kind
+    need_dx = kind != "stem"
+    xd, wd = x.double().requires_grad_(need_dx), w.double().requires_grad_(True)
+    yd = F.conv2d(xd, wd, stride=st, padding=pd)
+    dy = torch.randn(yd.shape, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    yd.backward(dy.double())
+    x1, w1 = x.clone().requires_grad_(need_dx), w.clone().requires_grad_(True)
+    y1 = conv_tc.conv2d(x1, w1, None, (st, st), (pd, pd), (1, 1), 1)
+    y1.backward(dy)
+    x2, w2 = x.clone().requires_grad_(need_dx), w.clone().requires_grad_(True)
+    y2 = F.conv2d(x2, w2, stride=st, padding=pd)
+    y2.backward(dy)
+    trip = [("y", y1, y2, yd.detach()), ("dw", w1.grad, w2.grad, wd.grad)]
+    if need_dx:
+        trip.append(("dx", x1.grad, x2.grad, xd.grad))
+    for name, ours, ref32, truth in trip:
+        e_ours, e_ref = _rms(ours, truth), _rms(ref32, truth)
+        print(f"{kind} {name} {N}x{H}x{W} {Ci}->{Co}: rms err ours {e_ours:.3e} cudnn-fp32 {e_ref:.3e} | max ours "
+              f"{_rel(ours, truth):.3e} cudnn {_rel(ref32, truth):.3e}")
+        assert ours.shape == truth.shape, name
+        assert e_ours < 5e-7 and e_ours <= 4 * e_ref + 1e-8, name
+        assert _rel(ours, truth) < 4e-6, name
+    assert w1.grad.stride() == w1.stride()
+
+
 def test_wgrad_is_bitwise_reproducible():
     x, w, dy = _mk(4, 16, 16, 128, 128, seed=2)
     outs = []
@@ -104,12 +148,27 @@ def test_wgrad_is_bitwise_reproducible():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
-def test_resnet_block_uses_the_tensor_core_conv():
-    from eventgrad_b200.models.resnet import BasicBlock
+def test_whole_resnet_runs_on_the_tensor_core_convs_and_matches_cudnn():
+    """every conv of the reference ResNet (stem, 3x3 s1/s2, 1x1 s2) takes the tcgen05 path; loss and gradients agree
+    with the cuDNN fp32 run of the same model to fp32 round-off"""
+    from eventgrad_b200.models.resnet import make_resnet
     from eventgrad_b200.ops import ext
-    blk = BasicBlock(64, 64).cuda().to(memory_format=torch.channels_last)
-    x = torch.randn(8, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    before = dict(ext().launch_counts())["conv"]
-    blk(x).sum().backward()
-    assert dict(ext().launch_counts())["conv"] > before
-    assert x.grad is not None and torch.isfinite(x.grad).all()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    m = make_resnet("resnet18").cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(16, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device="cuda")
+    res = {}
+    for on in (True, False):
+        conv_tc.set_enabled(on)
+        m.zero_grad(set_to_none=True)
+        before = dict(ext().launch_counts())["conv"]
+        loss = F.cross_entropy(m(x), y)
+        loss.backward()
+        n = dict(ext().launch_counts())["conv"] - before
+        res[on] = (float(loss), torch.cat([p.grad.flatten() for p in m.parameters()]).clone(), n)
+    conv_tc.set_enabled(None)
+    assert res[True][2] >= 28 * 3 and res[False][2] == 0          # 28 convs: fprop + dgrad + wgrad launches (+ splits)
+    assert abs(res[True][0] - res[False][0]) < 1e-5 * max(1.0, abs(res[False][0]))
+    ga, gb = res[True][1].double(), res[False][1].double()
+    assert float((ga - gb).norm() / gb.norm()) < 2e-5             # two fp32 runs of a 28-conv network

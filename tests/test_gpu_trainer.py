@@ -120,15 +120,17 @@ def test_p2p_file_write_logs(tmp_path):
 
 
 def test_gpu_defaults_are_the_fast_path_and_fp32_uses_fused_bn():
-    """No execution flags: on a GPU the Trainer runs NHWC + whole-step CUDA graph, and the fp32 activations go through
-    the fused BN kernels (csrc/bn_act.cu instantiated for float) -- counted through the extension's launch counter."""
+    """No execution flags: on a GPU the Trainer runs NHWC + whole-step CUDA graph; the fp32 activations go through
+    the fused BN kernels (csrc/bn_act.cu instantiated for float) and the fp32 convolutions through the tcgen05 kernels
+    (csrc/conv_tc.cu) -- counted through the extension's launch counter."""
     from eventgrad_b200.ops import ext
     C = ext()
     n0 = C.launch_count()
     tr, _ = _run(steps=6)                               # dtype defaults to fp32
-    assert tr.cfg.dtype == "fp32" and tr.cfg.cuda_graph and not tr.cfg.channels_last
+    assert tr.cfg.dtype == "fp32" and tr.cfg.cuda_graph and tr.cfg.channels_last and tr.cfg.conv_tc
     assert len(tr._graphs) == 1
     per_step = tr.own_launches_per_step
     assert per_step.get("bn", 0) >= 4 * 13 and per_step.get("gossip", 0) >= 1, per_step
+    assert per_step.get("conv", 0) >= 3 * 13, per_step      # every conv of the model: fprop + dgrad + wgrad (+ splits)
     assert C.launch_count() > n0
     tr.close()
