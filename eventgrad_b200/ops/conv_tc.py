@@ -172,16 +172,19 @@ def eligible(x, weight, stride, padding, dilation, groups) -> bool:
 
 
 # A down-sampling block feeds the SAME tensor to its 3x3/stride-2 conv and to its 1x1/stride-2 down-sampler: split it
-# once.  The strong reference keeps `id(x)` from being recycled while the entry is alive.
-_PARITY_CACHE = {"x": None, "ver": -1, "planes": None}
+# once.  Only a WEAK reference to the activation is kept: a strong one would keep its autograd graph -- and the
+# AccumulateGrad nodes of every earlier layer, bound to the stream of the step that built them -- alive into the
+# next step (which breaks CUDA-graph capture); a dead weakref can never match a recycled id().
+_PARITY_CACHE = {"ref": None, "ver": -1, "planes": None}
 
 
 def _parity_planes(x: torch.Tensor) -> torch.Tensor:
+    import weakref
     c = _PARITY_CACHE
-    if c["x"] is x and c["ver"] == x._version:
+    if c["ref"] is not None and c["ref"]() is x and c["ver"] == x._version:
         return c["planes"]
     planes = split3_parity(x.permute(0, 2, 3, 1))
-    c["x"], c["ver"], c["planes"] = x, x._version, planes
+    c["ref"], c["ver"], c["planes"] = weakref.ref(x), x._version, planes
     return planes
 
 
