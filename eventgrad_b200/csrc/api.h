@@ -232,6 +232,10 @@ struct BnParams {
   float momentum;
   int relu;
   int fused_ok;               // allow the single-launch fused path when the grid is co-resident
+  // fp32 only, optional: ALSO emit the result as three bf16 planes [3][M*C] (x = p0+p1+p2) -- the operand format of
+  // the tensor-core convolutions (csrc/conv_tc.cu), so the consumer conv needs no separate split pass
+  __nv_bfloat16* y_planes;    // forward: planes of y
+  __nv_bfloat16* dx_planes;   // backward: planes of dx (= dY of the convolution that produced x)
 };
 int bn_partial_rows(int sm_count);
 // fp32 NCHW variant (csrc/bn_nchw.cu): `hw` = H*W (multiple of 4), p.M = N*H*W.  Workspace: p.partial >= C*64*2
@@ -266,10 +270,14 @@ struct ConvTcParams {
   int ntaps, nsrc, wtaps;   // taps of this launch, source sub-images per plane, taps in the weight matrix
   signed char dh[9], dw[9], src[9], wk[9];
   int OH, OW, os, op, oq;   // fprop: pixel (n,i,j) -> out[n][i*os+op][j*os+oq]
+  float* ws;                // fprop: workspace [ksplits][m_tiles*128][Cb] when ksplits > 1
+  int ksplits;              // fprop: K-loop splits (conv_fprop_ksplits(); 1 = none)
   int bh, bn, m_tiles, k_blocks;   // filled in by the launchers
 };
 bool conv_tc_supported(int N, int H, int W, int Ca, int Cb);
 int conv_wgrad_splits(int N, int H, int W, int Ca, int Cb, int ntaps, int sm_count);
+int conv_fprop_ksplits(int N, int H, int W, int Ca, int Cb, int ntaps, int sm_count);
+int conv_fprop_mtiles(int N, int H, int W);   // 128-pixel tiles of the grid (workspace rows = 128 * this)
 cudaError_t launch_conv_fprop(const ConvTcParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_conv_wgrad(const ConvTcParams& p, float* dw, int splits, cudaStream_t s);
 cudaError_t launch_split3(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s);   // n % 8 == 0

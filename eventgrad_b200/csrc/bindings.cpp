@@ -205,7 +205,7 @@ PYBIND11_MODULE(_C, m) {
                          uintptr_t invstd, uintptr_t run_mean, uintptr_t run_var, uintptr_t nbt, uintptr_t partial,
                          uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
                          float eps, float momentum, int relu, int training, int fused_ok, int sm_count, int fp32,
-                         int nchw_hw, uintptr_t s) {
+                         int nchw_hw, uintptr_t s, uintptr_t y_planes) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
     p.fp32 = fp32;
@@ -225,6 +225,8 @@ PYBIND11_MODULE(_C, m) {
     p.epoch = reinterpret_cast<unsigned int*>(epoch);
     p.status = reinterpret_cast<int*>(status);
     p.M = M; p.C = C; p.eps = eps; p.momentum = momentum; p.relu = relu; p.fused_ok = fused_ok;
+    if (y_planes != 0 && (!fp32 || nchw_hw > 0)) throw std::invalid_argument("bn_forward: planes need the fp32 NHWC path");
+    p.y_planes = reinterpret_cast<__nv_bfloat16*>(y_planes);
     if (nchw_hw > 0)
       check(launch_bn_nchw(p, nchw_hw, training ? 0 : 1, sm_count, S(s)), "bn_forward (nchw)");
     else
@@ -233,7 +235,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("bn_backward", [](uintptr_t x, uintptr_t y, uintptr_t dy, uintptr_t dx, uintptr_t dres, uintptr_t gamma,
                           uintptr_t mean, uintptr_t invstd, uintptr_t dgamma, uintptr_t dbeta, uintptr_t partial,
                           uintptr_t ticket, uintptr_t flag, uintptr_t epoch, uintptr_t status, long long M, int C,
-                          int relu, int fused_ok, int sm_count, int fp32, int nchw_hw, uintptr_t s) {
+                          int relu, int fused_ok, int sm_count, int fp32, int nchw_hw, uintptr_t s,
+                          uintptr_t dx_planes) {
     BnParams p;
     std::memset(&p, 0, sizeof(p));
     p.fp32 = fp32;
@@ -253,6 +256,8 @@ PYBIND11_MODULE(_C, m) {
     p.epoch = reinterpret_cast<unsigned int*>(epoch);
     p.status = reinterpret_cast<int*>(status);
     p.M = M; p.C = C; p.relu = relu; p.fused_ok = fused_ok;
+    if (dx_planes != 0 && (!fp32 || nchw_hw > 0)) throw std::invalid_argument("bn_backward: planes need the fp32 NHWC path");
+    p.dx_planes = reinterpret_cast<__nv_bfloat16*>(dx_planes);
     if (nchw_hw > 0)
       check(launch_bn_nchw(p, nchw_hw, 2, sm_count, S(s)), "bn_backward (nchw)");
     else
@@ -272,6 +277,10 @@ PYBIND11_MODULE(_C, m) {
   m.def("conv_wgrad_splits", [](int N, int H, int W, int Ca, int Cb, int ntaps, int sm) {
     return conv_wgrad_splits(N, H, W, Ca, Cb, ntaps, sm);
   });
+  m.def("conv_fprop_ksplits", [](int N, int H, int W, int Ca, int Cb, int ntaps, int sm) {
+    return conv_fprop_ksplits(N, H, W, Ca, Cb, ntaps, sm);
+  });
+  m.def("conv_fprop_mtiles", [](int N, int H, int W) { return conv_fprop_mtiles(N, H, W); });
   m.def("split3", [](uintptr_t src, uintptr_t dst, size_t n, uintptr_t s) {
     check(launch_split3(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), n, S(s)), "split3");
   });
@@ -300,13 +309,14 @@ PYBIND11_MODULE(_C, m) {
   };
   m.def("conv_fprop", [fill](uintptr_t a, uintptr_t b, uintptr_t out, int N, int H, int W, int Ca, int Cb,
                              std::vector<std::tuple<int, int, int, int>> taps, int nsrc, int wtaps, int OH, int OW, int os,
-                             int op, int oq, int sm_count, uintptr_t s) {
+                             int op, int oq, int sm_count, uintptr_t s, uintptr_t ws, int ksplits) {
     ConvTcParams p{};
     p.a = reinterpret_cast<const __nv_bfloat16*>(a);
     p.b = reinterpret_cast<const __nv_bfloat16*>(b);
     p.out = reinterpret_cast<float*>(out);
     p.N = N; p.H = H; p.W = W; p.Ca = Ca; p.Cb = Cb; p.nsrc = nsrc; p.wtaps = wtaps;
     p.OH = OH; p.OW = OW; p.os = os; p.op = op; p.oq = oq;
+    p.ws = reinterpret_cast<float*>(ws); p.ksplits = ksplits;
     fill(p, taps);
     check(launch_conv_fprop(p, sm_count, S(s)), "conv_fprop");
   });

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_fwd_apply_kernel(const BnPar
       Raw8<T> o;
       pack8(x, o);
       st8(py + r2 * p.C + coff, o);
+      if (p.y_planes != nullptr) store_planes8(x, p.y_planes + r2 * p.C + coff, (size_t)p.M * p.C);
     }
   }
 }
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_dx_kernel(const BnParams
       Raw8<T> o;
       pack8(x, o);
       st8(pdx + r2 * p.C + coff, o);
+      if (p.dx_planes != nullptr) store_planes8(x, p.dx_planes + r2 * p.C + coff, (size_t)p.M * p.C);
       if (want_dres) {
         pack8(d, o);
         st8(pdres + r2 * p.C + coff, o);
@@ -422,7 +424,7 @@ static cudaError_t launch_bn_t(const BnParams& p, int which, int sm_count, cudaS
   };
   if (which == 0) {
     const long long rs_f = ceil_div(passes, BN_FWD_PASSES);
-    if (p.fused_ok && rs_f * slices <= max_ctas) {
+    if (p.fused_ok && p.y_planes == nullptr && rs_f * slices <= max_ctas) {
       eg_count_launch(EG_FAM_BN, 1);
       bn_fwd_fused_kernel<T><<<dim3((unsigned)slices, (unsigned)rs_f), BN_THREADS, 0, s>>>(p);
     } else {
@@ -435,7 +437,7 @@ static cudaError_t launch_bn_t(const BnParams& p, int which, int sm_count, cudaS
     bn_fwd_apply_kernel<T><<<map_grid(BN_APPLY_UNROLL(T)), BN_THREADS, 0, s>>>(p);
   } else if (which == 2) {
     const long long rs_b = ceil_div(passes, BN_BWD_PASSES);
-    if (p.fused_ok && rs_b * slices <= max_ctas) {
+    if (p.fused_ok && p.dx_planes == nullptr && rs_b * slices <= max_ctas) {
       eg_count_launch(EG_FAM_BN, 1);
       bn_bwd_fused_kernel<T><<<dim3((unsigned)slices, (unsigned)rs_b), BN_THREADS, 0, s>>>(p);
     } else {

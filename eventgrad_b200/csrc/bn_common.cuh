@@ -34,6 +34,21 @@ __device__ __forceinline__ uint4 pack_bf16x8(const V8& r) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
   return u;
 }
+// fp32 -> three bf16 planes (x = a + b + c to 2^-24 |x|; both residuals are exact in fp32) for 8 values; `base` points at
+// plane 0 of these 8 elements, the other planes are `plane` elements further (csrc/conv_tc.cu operand format)
+__device__ __forceinline__ void store_planes8(const V8& x, __nv_bfloat16* base, size_t plane) {
+  __nv_bfloat16 a[8], b[8], c[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = __float2bfloat16_rn(x.v[e]);
+    const float r1 = __fsub_rn(x.v[e], __bfloat162float(a[e]));
+    b[e] = __float2bfloat16_rn(r1);
+    c[e] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(b[e])));
+  }
+  *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(a);
+  *reinterpret_cast<uint4*>(base + plane) = *reinterpret_cast<const uint4*>(b);
+  *reinterpret_cast<uint4*>(base + 2 * plane) = *reinterpret_cast<const uint4*>(c);
+}
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& u) { *reinterpret_cast<uint4*>(p) = u; }
 

@@ -66,10 +66,16 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   constexpr uint32_t NCOLS = 2u * NT;                      // two accumulators (128 or 256 columns: powers of two)
-  const int cpb = p.Ca / 64, num_kb = p.ntaps * cpb;
+  const int cpb = p.Ca / 64, num_kb_all = p.ntaps * cpb;
   const int n_tiles = p.Cb / NT;
-  const int total = p.m_tiles * n_tiles;
+  const int ksplits = p.ksplits;                           // > 1: few tiles (small batch): split the K loop over CTAs,
+  const int kper = (num_kb_all + ksplits - 1) / ksplits;   //      partial tiles go to a workspace (launcher reduces)
+  const int total = p.m_tiles * n_tiles * ksplits;
   const int tpi = p.bn == 1 ? p.H / p.bh : 1;              // tiles per image
+#define CV_DECODE_WORK                                                         \
+  const int ks = work % ksplits, tile_ = work / ksplits;                       \
+  const int mt = tile_ / n_tiles, nt = tile_ - mt * n_tiles;                   \
+  const int kb_lo = ks * kper, kb_hi = min(num_kb_all, kb_lo + kper);
 
   if (warp == 2) tmem_alloc(s_u32(tmem_slot), NCOLS);
   if (tid == 0) {
@@ -93,10 +99,10 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       uint32_t it = 0;
       for (int work = blockIdx.x; work < total; work += gridDim.x) {
-        const int mt = work / n_tiles, nt = work - mt * n_tiles;
+        CV_DECODE_WORK
         const int n0 = p.bn == 1 ? mt / tpi : mt * p.bn;
         const int h0 = p.bn == 1 ? (mt - n0 * tpi) * p.bh : 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           const int tap = kb / cpb, cc = kb - tap * cpb;
           const int dh = p.dh[tap], dw = p.dw[tap], src = p.src[tap], wk = p.wk[tap];
@@ -118,7 +124,9 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t idesc = idesc_bf16_f32(128, NT, 0, 0);
       uint32_t it = 0;
       for (int work = blockIdx.x; work < total; work += gridDim.x) {
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        CV_DECODE_WORK
+        (void)mt; (void)nt;
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
           bar_wait(full0 + 8u * s, ph);                          // operands have landed
@@ -150,11 +158,11 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t it = 0;
     const long long M = (long long)p.N * p.H * p.W;
     for (int work = blockIdx.x; work < total; work += gridDim.x) {
-      const int mt = work / n_tiles, nt = work - mt * n_tiles;
+      CV_DECODE_WORK
       float acc[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[j] = 0.f;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
         bar_wait(tfull0 + 8u * as, aph);
         tmem_fence_after();
@@ -170,7 +178,11 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) bar_arrive(tempty0 + 8u * as);
       }
       const long long row = (long long)mt * 128 + q * 32 + lane;
-      if (row < M) {
+      if (ksplits > 1) {                                       // partial tile, dense rows: ws[ks][m_tiles*128][Cb]
+        float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)ks * p.m_tiles * 128) + (size_t)row) * p.Cb + nt * NT);
+#pragma unroll
+        for (int j = 0; j < NT / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      } else if (row < M) {
         long long opix = row;
         if (p.os != 1 || p.OH != p.H || p.OW != p.W) {          // strided scatter (data gradient of a stride-2 conv)
           const int hw = p.H * p.W;
@@ -187,6 +199,30 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tmem_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, NCOLS);
+}
+
+// out[pixel(row)][c] = sum_ks ws[ks][row][c] (fixed order), with the same output mapping as the un-split epilogue
+__global__ void __launch_bounds__(256) conv_fprop_reduce_kernel(const ConvTcParams p) {
+  const long long M = (long long)p.N * p.H * p.W;
+  const int c4n = p.Cb / 4;
+  const size_t zs = (size_t)p.m_tiles * 128 * p.Cb;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * c4n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c4n;
+    const int c4 = (int)(i - row * c4n);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < p.ksplits; ++z) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.ws + z * zs + (size_t)row * p.Cb) + c4);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    long long opix = row;
+    if (p.os != 1 || p.OH != p.H || p.OW != p.W) {
+      const int hw = p.H * p.W;
+      const int n = (int)(row / hw), rem = (int)(row - (long long)n * hw);
+      const int ii = rem / p.W, j = rem - ii * p.W;
+      opix = ((long long)n * p.OH + ii * p.os + p.op) * p.OW + j * p.os + p.oq;
+    }
+    reinterpret_cast<float4*>(p.out + (size_t)opix * p.Cb)[c4] = a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -525,6 +561,25 @@ static bool taps_ok(const ConvTcParams& p) {
   return true;
 }
 
+// K-loop splits of the forward kernel: only when the tiles alone leave most SMs idle (small per-GPU batch)
+int conv_fprop_ksplits(int N, int H, int W, int Ca, int Cb, int ntaps, int sm_count) {
+  int bh, bn, m_tiles;
+  if (!tile_geometry(N, H, W, 128, &bh, &bn, &m_tiles)) return 0;
+  const int NT = (Cb % 128 == 0) ? 128 : 64;
+  const int tiles = m_tiles * (Cb / NT), num_kb = ntaps * (Ca / 64);
+  if (tiles * 2 > sm_count || num_kb < 4) return 1;
+  int ks = sm_count / tiles;
+  if (ks > num_kb / 2) ks = num_kb / 2;                     // at least two k-blocks per split
+  if (ks < 2) return 1;
+  const int per = (num_kb + ks - 1) / ks;
+  return (num_kb + per - 1) / per;                          // no empty split
+}
+
+int conv_fprop_mtiles(int N, int H, int W) {
+  int bh, bn, m_tiles;
+  return tile_geometry(N, H, W, 128, &bh, &bn, &m_tiles) ? m_tiles : 0;
+}
+
 template <int NT, int STAGES>
 static cudaError_t fprop_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int grid,
                                 cudaStream_t s) {
@@ -542,14 +597,25 @@ cudaError_t launch_conv_fprop(const ConvTcParams& p0, int sm_count, cudaStream_t
   if (p.os < 1 || p.op < 0 || p.oq < 0 || p.op >= p.os || p.oq >= p.os || p.OH < p.H * p.os || p.OW < p.W * p.os)
     return cudaErrorInvalidValue;
   tile_geometry(p.N, p.H, p.W, 128, &p.bh, &p.bn, &p.m_tiles);
+  if (p.ksplits < 1 || p.ws == nullptr) p.ksplits = 1;
+  if (p.ksplits > 1) {                                      // the caller sized ws with conv_fprop_ksplits()
+    const int want = conv_fprop_ksplits(p.N, p.H, p.W, p.Ca, p.Cb, p.ntaps, sm_count);
+    if (p.ksplits != want) return cudaErrorInvalidValue;
+  }
   CUtensorMap tmA, tmB;
   const int NT = (p.Cb % 128 == 0) ? 128 : 64;
   if (!make_map_act(&tmA, p.a, p.Ca, p.W, p.H, p.N, 3 * p.nsrc, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
   if (!make_map_w(&tmB, p.b, (uint64_t)p.wtaps * p.Ca, (uint64_t)3 * p.Cb, (uint32_t)NT)) return cudaErrorNotSupported;
-  const int total = p.m_tiles * (p.Cb / NT);
+  const int total = p.m_tiles * (p.Cb / NT) * p.ksplits;
   const int grid = total < sm_count ? total : sm_count;
-  eg_count_launch(EG_FAM_CONV, 1);
-  return NT == 128 ? fprop_launch<128, 2>(tmA, tmB, p, grid, s) : fprop_launch<64, 3>(tmA, tmB, p, grid, s);
+  eg_count_launch(EG_FAM_CONV, p.ksplits > 1 ? 2 : 1);
+  cudaError_t e = NT == 128 ? fprop_launch<128, 2>(tmA, tmB, p, grid, s) : fprop_launch<64, 3>(tmA, tmB, p, grid, s);
+  if (e != cudaSuccess || p.ksplits == 1) return e;
+  const long long n4 = (long long)p.N * p.H * p.W * (p.Cb / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_fprop_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
+  return cudaGetLastError();
 }
 
 template <int NT, int STAGES>

@@ -83,6 +83,23 @@ class ResNet(nn.Module):
         self.layer3 = self._make_layer(block, 256, layers[2], 2)
         self.layer4 = self._make_layer(block, 512, layers[3], 2)
         self.fc = ShadowLinear(512 * block.expansion, classes)
+        self._mark_plane_emitters()
+
+    def _mark_plane_emitters(self) -> None:
+        """BN layers whose output feeds a stride-1 convolution write it ALSO as bf16 planes (ops/bn_act.py
+        emit_planes): inside a block every BN but the last, and a block's last BN when the NEXT block starts with a
+        stride-1 conv that is the only conv reading it (no down-sampler: those read parity planes instead)."""
+        blocks = [b for layer in (self.layer1, self.layer2, self.layer3, self.layer4) for b in layer]
+        prev_last = self.bn
+        for b in blocks:
+            convs = [m for m in (getattr(b, "conv1", None), getattr(b, "conv2", None), getattr(b, "conv3", None))
+                     if m is not None]
+            bns = [m for m in (getattr(b, "bn1", None), getattr(b, "bn2", None), getattr(b, "bn3", None)) if m is not None]
+            if b.downsampler is None and tuple(convs[0].stride) == (1, 1):
+                prev_last.emit_planes = True
+            for bn, nxt in zip(bns[:-1], convs[1:]):
+                bn.emit_planes = tuple(nxt.stride) == (1, 1)
+            prev_last = bns[-1]
 
     def _make_layer(self, block, cout: int, blocks: int, stride: int) -> nn.Sequential:
         downsample = None

@@ -75,7 +75,8 @@ def _eligible(x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
 
 class _FusedBNActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, residual, training, momentum, eps, relu):
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, residual, training, momentum, eps, relu,
+                y_planes=None, dx_planes_wanted=False):
         ws = _workspace(x.device)
         C_ext = ws["C"]
         N, C, H, W = x.shape
@@ -101,7 +102,10 @@ class _FusedBNActFn(torch.autograd.Function):
                              ws["nchw_ticket"].data_ptr() if nchw else ws["f"][0], ws["f"][1], ws["f"][2],
                              ws["status"], M, C,
                              float(eps), float(momentum), 1 if relu else 0, 1 if training else 0, ws["fused"],
-                             ws["sm"], 1 if x.dtype == torch.float32 else 0, ctx.nchw_hw, stream)
+                             ws["sm"], 1 if x.dtype == torch.float32 else 0, ctx.nchw_hw, stream,
+                             y_planes.data_ptr() if (y_planes is not None and not nchw) else 0)
+        ctx.planes_emitted = y_planes is not None and not nchw
+        ctx.dx_planes = bool(dx_planes_wanted) and not nchw and x.dtype == torch.float32
         ctx.save_for_backward(x, y, weight, mean, invstd)
         ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
         return y
@@ -124,6 +128,7 @@ class _FusedBNActFn(torch.autograd.Function):
         dres = torch.empty_like(x) if ctx.has_res else None
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        dxp = torch.empty(3, x.numel(), dtype=torch.bfloat16, device=x.device) if ctx.dx_planes else None
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
             C_ext.bn_backward(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(),
@@ -132,8 +137,12 @@ class _FusedBNActFn(torch.autograd.Function):
                               (ws["nchw_partial"] if ctx.nchw_hw else ws["partial"]).data_ptr(),
                               ws["nchw_ticket"][2048:].data_ptr() if ctx.nchw_hw else ws["b"][0], ws["b"][1], ws["b"][2],
                               ws["status"], M, C, 1 if ctx.relu else 0,
-                              ws["fused"], ws["sm"], 1 if x.dtype == torch.float32 else 0, ctx.nchw_hw, stream)
-        return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None
+                              ws["fused"], ws["sm"], 1 if x.dtype == torch.float32 else 0, ctx.nchw_hw, stream,
+                              dxp.data_ptr() if dxp is not None else 0)
+        if dxp is not None:
+            from .conv_tc import planes_put
+            planes_put(dx, dxp)                     # the producing conv's backward finds its dY already split
+        return dx, dgamma, dbeta, None, None, None, dres, None, None, None, None, None, None
 
 
 def bn_act_reference(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu):
@@ -145,12 +154,27 @@ def bn_act_reference(x, weight, bias, running_mean, running_var, residual, train
 
 
 class FusedBNAct(nn.BatchNorm2d):
+    # set by the model (models/resnet.py) on layers whose output feeds a 3x3/stride-1 or 1x1/stride-1 convolution: in
+    # fp32 those run on the tensor cores from three bf16 planes, which the apply kernel can write on the way out
+    emit_planes = False
+
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
         training = self.training or (self.running_mean is None)
-        if (_eligible(x, residual) or _eligible_nchw(x, residual)) and self.affine and self.momentum is not None:
-            return _FusedBNActFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
-                                       self.num_batches_tracked if training else None, residual, training,
-                                       self.momentum, self.eps, relu)
+        nhwc = _eligible(x, residual)
+        if (nhwc or _eligible_nchw(x, residual)) and self.affine and self.momentum is not None:
+            yp, want_dxp = None, False
+            if nhwc and x.dtype == torch.float32:
+                from . import conv_tc
+                if conv_tc.enabled():
+                    want_dxp = bool(getattr(x, "_egb_tc", False)) and training and torch.is_grad_enabled()
+                    if self.emit_planes:
+                        yp = torch.empty(3, x.numel(), dtype=torch.bfloat16, device=x.device)
+            y = _FusedBNActFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                    self.num_batches_tracked if training else None, residual, training,
+                                    self.momentum, self.eps, relu, yp, want_dxp)
+            if yp is not None:
+                conv_tc.planes_put(y, yp)
+            return y
         if training and self.track_running_stats and self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
         return bn_act_reference(x, self.weight, self.bias, self.running_mean, self.running_var, residual,

@@ -47,6 +47,38 @@ def enabled() -> bool:
     return os.environ.get("EGB_CONV_TC", "1") != "0"
 
 
+# ------------------------------------------------------------------------------------------------ plane registry
+# The fused BN kernels (ops/bn_act.py) can emit their output ALSO as three bf16 planes: the activation that feeds the
+# next conv (forward) and the gradient that feeds the previous conv's backward.  They are handed over here, keyed by
+# the tensor's address and validated by object identity + version, so a conv that finds its operand already split
+# skips the split pass.  Entries die with the tensor (weakref callback); a miss is only a missed optimisation.
+_PLANES = {}
+
+
+def planes_put(t: torch.Tensor, planes: torch.Tensor) -> None:
+    import weakref
+    key = t.data_ptr()
+
+    def _gone(r, k=key):
+        e = _PLANES.get(k)
+        if e is not None and e[0] is r:
+            _PLANES.pop(k, None)
+    _PLANES[key] = (weakref.ref(t, _gone), t._version, planes)
+
+
+def planes_get(t: torch.Tensor):
+    e = _PLANES.get(t.data_ptr())
+    if e is not None and e[0]() is t and e[1] == t._version and e[2].numel() == 3 * t.numel():
+        return e[2]
+    return None
+
+
+def mark_tc_output(y: torch.Tensor) -> torch.Tensor:
+    """tag a conv output produced here: the BN that consumes it emits the planes of its input gradient"""
+    y._egb_tc = True
+    return y
+
+
 # ------------------------------------------------------------------------------------------------ tap tables
 # (dh, dw, source sub-image, weight slice).  Weight slices index the OHWI weight's tap axis (r*3 + s).
 TAPS_S1 = [(r - 1, s - 1, 0, r * 3 + s) for r in range(3) for s in range(3)]
@@ -116,15 +148,24 @@ def wprep(w_oti: torch.Tensor, transposed: bool):
     return wp, wtp
 
 
+KSPLIT = os.environ.get("EGB_CONV_KSPLIT", "1") != "0"
+
+
 def fprop(ap, wp, N, H, W, Ca, Cb, taps, nsrc=1, wtaps=9, out=None, OH=None, OW=None, os_=1, op=0, oq=0):
     """implicit GEMM over the pixel grid (N,H,W): out[n, i*os+op, j*os+oq, :] = sum_taps A_tap[n,i,j,:] @ W_tap^T"""
     from . import ext
+    C = ext()
     OH, OW = OH or H, OW or W
     if out is None:
         out = torch.empty(N, OH, OW, Cb, dtype=torch.float32, device=ap.device)
+    # few output tiles (small per-GPU batch): the K loop is split over CTAs, partial tiles summed by a second kernel
+    ks = C.conv_fprop_ksplits(N, H, W, Ca, Cb, len(taps), _sm(ap.device)) if KSPLIT else 1
+    ws = None
+    if ks > 1:
+        ws = torch.empty(ks, C.conv_fprop_mtiles(N, H, W) * 128, Cb, dtype=torch.float32, device=ap.device)
     with torch.cuda.device(ap.device):
-        ext().conv_fprop(ap.data_ptr(), wp.data_ptr(), out.data_ptr(), N, H, W, Ca, Cb, taps, nsrc, wtaps, OH, OW, os_,
-                         op, oq, _sm(ap.device), _stream(ap.device))
+        C.conv_fprop(ap.data_ptr(), wp.data_ptr(), out.data_ptr(), N, H, W, Ca, Cb, taps, nsrc, wtaps, OH, OW, os_,
+                     op, oq, _sm(ap.device), _stream(ap.device), 0 if ws is None else ws.data_ptr(), ks)
     return out
 
 
@@ -201,11 +242,15 @@ class _ConvTcFn(torch.autograd.Function):
             wp, wtp = wprep(w64, False)
             y = fprop(xp, wp, N, H, W, 64, Co, TAPS_1X1, 1, 1)
         elif kind == "s1":
-            xp = split3(x)
+            xp = planes_get(x)
+            if xp is None:
+                xp = split3(x)
             wp, wtp = wprep(w_ohwi.reshape(Co, 9, Ci), ctx.needs_input_grad[0])
             y = fprop(xp, wp, N, H, W, Ci, Co, TAPS_S1, 1, 9)
         elif kind == "p1":
-            xp = split3(x)
+            xp = planes_get(x)
+            if xp is None:
+                xp = split3(x)
             wp, wtp = wprep(w_ohwi.reshape(Co, 1, Ci), ctx.needs_input_grad[0])
             y = fprop(xp, wp, N, H, W, Ci, Co, TAPS_1X1, 1, 1)
         else:                                                           # s2 / p2: parity images of the input
@@ -223,7 +268,9 @@ class _ConvTcFn(torch.autograd.Function):
         kind = ctx.kind
         if dy.dtype != torch.float32 or not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.to(torch.float32).contiguous(memory_format=torch.channels_last)
-        gp = split3(dy)
+        gp = planes_get(dy)                                             # emitted by the BN backward that produced dy
+        if gp is None:
+            gp = split3(dy)
         dx = dw = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if kind == "stem":
@@ -269,7 +316,7 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias, stride, padding, dilatio
     if bias is None:
         kind = kind_of(x, weight, stride, padding, dilation, groups)
         if kind is not None:
-            return _ConvTcFn.apply(x, weight, kind)
+            return mark_tc_output(_ConvTcFn.apply(x, weight, kind))
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 

@@ -65,6 +65,17 @@ def test_tile_geometry():
     assert C.conv_wgrad_splits(256, 32, 32, 64, 64, 1, 148) == 148      # stem / 1x1: one unit pair
 
 
+def test_fprop_k_splits_only_for_small_grids():
+    C = ext()
+    assert C.conv_fprop_ksplits(256, 32, 32, 64, 64, 9, 148) == 1          # 2048 tiles: no split
+    assert C.conv_fprop_ksplits(256, 4, 4, 512, 512, 9, 148) == 1          # 128 tiles
+    ks = C.conv_fprop_ksplits(32, 4, 4, 512, 512, 9, 148)                  # 16 tiles, 72 k-blocks
+    assert ks == 9 and C.conv_fprop_mtiles(32, 4, 4) == 4
+    ks = C.conv_fprop_ksplits(32, 8, 8, 256, 256, 9, 148)                  # 32 tiles, 36 k-blocks -> 4 splits of 9
+    assert ks == 4
+    assert C.conv_fprop_ksplits(32, 16, 16, 64, 128, 1, 148) == 1          # 1x1 with one k-block: nothing to split
+
+
 def test_tap_tables():
     """the tap tables of ops/conv_tc.py against the definition of the strided convolution and its transpose"""
     from eventgrad_b200.ops import conv_tc as ct

@@ -24,6 +24,7 @@ CASES = [  # N, H, W, Cin, Cout
     (16, 4, 4, 512, 512),
     (5, 4, 4, 128, 64),      # 4x4 images, batch not a multiple of the 8-image tile: zero-filled tail
     (3, 8, 8, 64, 64),       # odd number of 2-image tiles
+    (40, 32, 32, 64, 64),    # 320 tiles: persistent CTAs walk several tiles, no K split (the small cases above all split K)
 ]
 
 
@@ -135,7 +136,8 @@ def test_strided_pointwise_and_stem_match_fp64(kind, N, H, W, Ci, Co, k, st, pd)
         assert ours.shape == truth.shape, name
         assert e_ours < 5e-7 and e_ours <= 4 * e_ref + 1e-8, name
         assert _rel(ours, truth) < 4e-6, name
-    assert w1.grad.stride() == w1.stride()
+    # same memory order as the parameter (strides of size-1 dims are arbitrary)
+    assert [s_ for s_, n in zip(w1.grad.stride(), w1.shape) if n > 1] == [s_ for s_, n in zip(w1.stride(), w1.shape) if n > 1]
 
 
 def test_wgrad_is_bitwise_reproducible():
@@ -148,16 +150,23 @@ def test_wgrad_is_bitwise_reproducible():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
-def test_whole_resnet_runs_on_the_tensor_core_convs_and_matches_cudnn():
-    """every conv of the reference ResNet (stem, 3x3 s1/s2, 1x1 s2) takes the tcgen05 path; loss and gradients agree
-    with the cuDNN fp32 run of the same model to fp32 round-off"""
+def test_whole_resnet_runs_on_the_tensor_core_convs_and_is_as_close_to_fp64_as_cudnn():
+    """every conv of the reference ResNet (stem, 3x3 s1/s2, 1x1 s2) takes the tcgen05 path, BN hands the bf16 planes
+    over (no split pass between BN and the next conv), and the gradients of the whole network are as close to an fp64
+    run of the same model as the gradients of the cuDNN fp32 run are (a 28-conv BN network amplifies round-off, so
+    the two fp32 runs are compared against the TRUTH, not against each other)"""
+    import copy
     from eventgrad_b200.models.resnet import make_resnet
     from eventgrad_b200.ops import ext
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
     m = make_resnet("resnet18").cuda().to(memory_format=torch.channels_last)
-    x = torch.randn(16, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
-    y = torch.randint(0, 10, (16,), device="cuda")
+    x = torch.randn(32, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (32,), device="cuda")
+    m64 = copy.deepcopy(m).double()
+    l64 = F.cross_entropy(m64(x.double()), y)
+    l64.backward()
+    g64 = torch.cat([p.grad.flatten() for p in m64.parameters()])
     res = {}
     for on in (True, False):
         conv_tc.set_enabled(on)
@@ -166,9 +175,13 @@ def test_whole_resnet_runs_on_the_tensor_core_convs_and_matches_cudnn():
         loss = F.cross_entropy(m(x), y)
         loss.backward()
         n = dict(ext().launch_counts())["conv"] - before
-        res[on] = (float(loss), torch.cat([p.grad.flatten() for p in m.parameters()]).clone(), n)
+        g = torch.cat([p.grad.flatten() for p in m.parameters()]).double()
+        res[on] = (abs(float(loss) - float(l64)), float((g - g64).norm() / g64.norm()), n)
     conv_tc.set_enabled(None)
-    assert res[True][2] >= 28 * 3 and res[False][2] == 0          # 28 convs: fprop + dgrad + wgrad launches (+ splits)
-    assert abs(res[True][0] - res[False][0]) < 1e-5 * max(1.0, abs(res[False][0]))
-    ga, gb = res[True][1].double(), res[False][1].double()
-    assert float((ga - gb).norm() / gb.norm()) < 2e-5             # two fp32 runs of a 28-conv network
+    print(f"resnet18-ref vs fp64: |dloss| ours {res[True][0]:.2e} cudnn {res[False][0]:.2e}; grad rel err ours "
+          f"{res[True][1]:.3e} cudnn {res[False][1]:.3e}; conv-family launches {res[True][2]}")
+    assert res[False][2] == 0 and res[True][2] >= 28 * 3          # 28 convs: fprop + dgrad + wgrad (+ prep / splits)
+    # plane hand-over: 21 forward and 28 backward split passes are gone (only the parity / stem gathers remain)
+    assert res[True][2] <= 28 * 3 + 28 + 28 + 12 + 10
+    assert res[True][0] <= 3 * res[False][0] + 2e-6
+    assert res[True][1] <= 2 * res[False][1] + 1e-6
