@@ -35,15 +35,18 @@ def timed(fn, env, iters, warm=5):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    # the NVML counter read takes tens of ms and differs per rank: do it BEFORE the barrier, or the ranks enter the
+    # timed region skewed and the first launch of the fast ranks spins on the slow one (seen as +2.4 ms/launch at R=8)
+    c0 = NVL.read() if (NVL is not None and NVL.ok) else None
     barrier(env)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    c0 = NVL.read() if (NVL is not None and NVL.ok) else None
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
+    barrier(env)                       # every rank's traffic has landed before anybody reads its counters
     c1 = NVL.read() if c0 is not None else None
     LAST_NVLINK.clear()
     if c0 is not None and c1 is not None:

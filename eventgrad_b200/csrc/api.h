@@ -270,6 +270,7 @@ struct ConvTcParams {
   int ntaps, nsrc, wtaps;   // taps of this launch, source sub-images per plane, taps in the weight matrix
   signed char dh[9], dw[9], src[9], wk[9];
   int OH, OW, os, op, oq;   // fprop: pixel (n,i,j) -> out[n][i*os+op][j*os+oq]
+  float* dwout;             // wgrad: [Cb][ntaps*Ca] (OHWI); written directly by the kernel when there is one split
   float* ws;                // fprop: workspace [ksplits][m_tiles*128][Cb] when ksplits > 1
   int ksplits;              // fprop: K-loop splits (conv_fprop_ksplits(); 1 = none)
   int bh, bn, m_tiles, k_blocks;   // filled in by the launchers

@@ -345,10 +345,17 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (lane == 0) bar_arrive(tempty0 + 8u * as);
     }
     if (store) {
-      float4* dst = reinterpret_cast<float4*>(
-          p.out + ((size_t)blockIdx.z * (p.ntaps * p.Ca) + (size_t)unit * 64 + (m & 63)) * p.Cb + blockIdx.y * NT);
+      const size_t rows_all = (size_t)p.ntaps * p.Ca, my_row = (size_t)unit * 64 + (m & 63);
+      if (gridDim.z == 1) {
+        // one pixel split: this tile IS the result -- write dW[co][row] (OHWI) directly; lanes = consecutive rows
+        float* dw = p.dwout + (size_t)(blockIdx.y * NT) * rows_all + my_row;
 #pragma unroll
-      for (int j = 0; j < NT / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        for (int j = 0; j < NT; ++j) dw[(size_t)j * rows_all] = acc[j];
+      } else {
+        float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)blockIdx.z * rows_all + my_row) * p.Cb + blockIdx.y * NT);
+#pragma unroll
+        for (int j = 0; j < NT / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      }
     }
   }
   tmem_fence_before();
@@ -362,15 +369,29 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
   const int row0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const size_t zs = (size_t)rows * Cb;
-  for (int z = 0; z < splits; ++z) {
+  // sum over the splits as four interleaved chains (z mod 4) combined by a fixed tree: 16 loads in flight per thread
+  // instead of 4 (the kernel is latency bound), and still bitwise reproducible
+  float a4[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = row0 + ty + 8 * i;
-      if (r < rows) acc[i] += __ldg(ws + z * zs + (size_t)r * Cb + co0 + tx);
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a4[i][c] = 0.f;
+  const size_t zs = (size_t)rows * Cb;
+  for (int z0 = 0; z0 < splits; z0 += 4) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (z0 + c < splits) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + ty + 8 * i;
+          if (r < rows) a4[i][c] += __ldg(ws + (size_t)(z0 + c) * zs + (size_t)r * Cb + co0 + tx);
+        }
+      }
     }
   }
+  float acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = (a4[i][0] + a4[i][1]) + (a4[i][2] + a4[i][3]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = acc[i];
   __syncthreads();
@@ -641,9 +662,10 @@ cudaError_t launch_conv_wgrad(const ConvTcParams& p0, float* dw, int splits, cud
   if (!make_map_act(&tmG, p.b, p.Cb, p.W, p.H, p.N, 3, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
   const int U = p.ntaps * (p.Ca / 64);
   const dim3 grid((U + 1) / 2, p.Cb / NT, splits);
-  eg_count_launch(EG_FAM_CONV, 2);
+  p.dwout = dw;
+  eg_count_launch(EG_FAM_CONV, splits > 1 ? 2 : 1);
   cudaError_t e = NT == 128 ? wgrad_launch<128, 2>(tmX, tmG, p, grid, s) : wgrad_launch<64, 3>(tmX, tmG, p, grid, s);
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess || splits == 1) return e;
   const int rows = p.ntaps * p.Ca;
   conv_wgrad_reduce_kernel<<<dim3((rows + 31) / 32, p.Cb / 32), 256, 0, s>>>(p.out, dw, rows, p.Cb, splits);
   return cudaGetLastError();

@@ -2,7 +2,7 @@
 # tensor-core fp32 conv integrated into the Trainer: GPU tests, headline bench (+ cuDNN-fp32 / bf16 / tf32 rows), batch-32 proxy, kernel table
 O=gpurun_out/r2_conv2; mkdir -p $O
 python -m eventgrad_b200.build_ext > $O/build.txt 2>&1
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 -x -k "not multigpu" > $O/pytest.txt 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest.txt | cut -c1-300
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 -k "not multigpu" > $O/pytest.txt 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest.txt | cut -c1-300
 show() { grep '^{"metric"' $1 | tail -1 | python -c "
 import sys,json
 try:

@@ -181,7 +181,9 @@ def test_whole_resnet_runs_on_the_tensor_core_convs_and_is_as_close_to_fp64_as_c
     print(f"resnet18-ref vs fp64: |dloss| ours {res[True][0]:.2e} cudnn {res[False][0]:.2e}; grad rel err ours "
           f"{res[True][1]:.3e} cudnn {res[False][1]:.3e}; conv-family launches {res[True][2]}")
     assert res[False][2] == 0 and res[True][2] >= 28 * 3          # 28 convs: fprop + dgrad + wgrad (+ prep / splits)
-    # plane hand-over: 21 forward and 28 backward split passes are gone (only the parity / stem gathers remain)
-    assert res[True][2] <= 28 * 3 + 28 + 28 + 12 + 10
+    # plane hand-over: 21 forward and 28 backward split passes are gone (only the parity / stem gathers remain):
+    # 28 x (fprop + wgrad + wgrad-reduce + weight prep) + 24 dgrad + 9 extra launches of the three 4-class stride-2
+    # dgrads + 4 gathers = 149, plus one reduce launch per K-split forward/dgrad at this small batch
+    assert res[True][2] <= 149 + 2 * 28
     assert res[True][0] <= 3 * res[False][0] + 2e-6
     assert res[True][1] <= 2 * res[False][1] + 1e-6
