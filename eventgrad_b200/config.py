@@ -196,6 +196,9 @@ def _add_common_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--dtype", default=None, choices=["fp32", "tf32", "bf16"])
     p.add_argument("--channels-last", action=argparse.BooleanOptionalAction, default=None, help="default: on for CUDA")
     p.add_argument("--cuda-graph", action=argparse.BooleanOptionalAction, default=None, help="default: on for CUDA")
+    p.add_argument("--conv-tc", action=argparse.BooleanOptionalAction, default=None,
+                   help="fp32: convolutions on the tcgen05 tensor cores at fp32 accuracy (default: on for CUDA); "
+                        "--no-conv-tc = cuDNN's SIMT fp32 kernels")
     p.add_argument("--no-cudnn-benchmark", dest="cudnn_benchmark", action="store_false", default=None)
     p.add_argument("--max-steps", type=int, default=None)
     p.add_argument("--log-dir", default=None)

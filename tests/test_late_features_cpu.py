@@ -26,12 +26,17 @@ def test_execution_switches_resolve_to_the_fast_path_on_cuda_only():
     c = parse_cli("cifar_event", ["0", "1", "1.0"])
     assert c.channels_last is None and c.cuda_graph is None and c.overlap_push is None
     g8 = c.resolved("cuda", 8)
-    assert not g8.channels_last and g8.cuda_graph and g8.overlap_push       # fp32: NCHW (cuDNN's fp32 convs are NCHW)
+    # fp32: tensor-core convolutions at fp32 accuracy (csrc/conv_tc.cu) on NHWC activations ...
+    assert g8.conv_tc and g8.channels_last and g8.cuda_graph and g8.overlap_push
+    # ... unless switched off: cuDNN's fp32 convs are NCHW kernels, so that path stays NCHW
+    off_tc = c.replace(conv_tc=False).resolved("cuda", 8)
+    assert not off_tc.conv_tc and not off_tc.channels_last
+    assert not c.replace(dtype="bf16").resolved("cuda", 8).conv_tc
     assert c.replace(dtype="bf16").resolved("cuda", 8).channels_last and c.replace(dtype="tf32").resolved("cuda", 1).channels_last
     g1 = c.resolved("cuda", 1)
     assert g1.cuda_graph and not g1.overlap_push
     cpu = c.resolved("cpu", 2)
-    assert not cpu.channels_last and not cpu.cuda_graph and not cpu.overlap_push
+    assert not cpu.channels_last and not cpu.cuda_graph and not cpu.overlap_push and not cpu.conv_tc
     off = parse_cli("cifar_event", ["0", "1", "1.0", "--no-overlap-push", "--no-cuda-graph"]).resolved("cuda", 8)
     assert off.overlap_push is False and off.cuda_graph is False
     assert not parse_cli("cifar_spevent", ["0", "1", "1.0", "10"]).resolved("cuda", 8).overlap_push
