@@ -44,6 +44,10 @@ namespace egb {
 using namespace tc;
 
 #define CV_THREADS 192
+// TMEM accumulator ring: all 512 columns (8 accumulators at N tile 64, 4 at 128).  With two, the MMA of k-block i+2
+// has to wait for the drain of k-block i (barrier wake-up + tcgen05.ld + 64-128 adds + arrive); a deeper ring takes that
+// latency off the MMA's critical path.  (Measured neutral at batch 256 -- see the A/B list in profiles/README.md 0a.)
+#define CV_NACC(NT) (512 / (NT))
 #define CV_APLANE 16384u   // one bf16 plane of an operand tile with 128 rows: 128 x 128 B
 
 // the six cross terms (plane of A, plane of B), largest last so that the small corrections are summed first
@@ -63,9 +67,10 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   unsigned char* smem_al = smem_raw + (smem0 - smem_unaligned);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE);
   const uint32_t full0 = s_u32(bars), empty0 = full0 + 8u * STAGES;
-  const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 16u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  constexpr uint32_t NCOLS = 2u * NT;                      // two accumulators (128 or 256 columns: powers of two)
+  constexpr uint32_t NACC = CV_NACC(NT);
+  const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 8u * NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
+  constexpr uint32_t NCOLS = NACC * NT;                    // the whole TMEM: 512 columns
   const int cpb = p.Ca / 64, num_kb_all = p.ntaps * cpb;
   const int n_tiles = p.Cb / NT;
   const int ksplits = p.ksplits;                           // > 1: few tiles (small batch): split the K loop over CTAs,
@@ -83,7 +88,7 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       bar_init(full0 + 8u * i, 1);
       bar_init(empty0 + 8u * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (int)NACC; ++i) {
       bar_init(tfull0 + 8u * i, 1);
       bar_init(tempty0 + 8u * i, 4);
     }
@@ -119,8 +124,8 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA ISSUER =====================
-    if (lane == 0) {
+    // ===================== MMA ISSUER (whole warp walks the loop, one elected lane issues) =====================
+    {
       const uint32_t idesc = idesc_bf16_f32(128, NT, 0, 0);
       uint32_t it = 0;
       for (int work = blockIdx.x; work < total; work += gridDim.x) {
@@ -128,9 +133,9 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         (void)mt; (void)nt;
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-          const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+          const uint32_t as = it % NACC, aph = (it / NACC) & 1u;
           bar_wait(full0 + 8u * s, ph);                          // operands have landed
-          bar_wait(tempty0 + 8u * as, aph ^ 1u);                 // the accumulator of k-block it-2 has been drained
+          bar_wait(tempty0 + 8u * as, aph ^ 1u);                 // the accumulator of k-block it-NACC has been drained
           tmem_fence_after();
           const uint32_t tmem_d = tmem_base + as * NT;
           const uint32_t sa = smem0 + s * STAGE;
@@ -138,17 +143,20 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           // growing linearly with K).  So each k-block starts a fresh accumulator that the epilogue warps add into
           // fp32 registers with round-to-nearest, and inside the k-block the five small correction terms come first:
           // only the last four MMAs (x0*w0) accumulate onto a full-magnitude value.
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int t = 0; t < 6; ++t) {
+            for (int t = 0; t < 6; ++t) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t da = desc_k_sw128(sa + CV_TERM_A(t) * CV_APLANE) + (uint64_t)(k4 * 2);
-              const uint64_t db = desc_k_sw128(sa + A_BYTES + CV_TERM_B(t) * B_PLANE) + (uint64_t)(k4 * 2);
-              umma_bf16(tmem_d, da, db, idesc, (k4 > 0 || t > 0) ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da = desc_k_sw128(sa + CV_TERM_A(t) * CV_APLANE) + (uint64_t)(k4 * 2);
+                const uint64_t db = desc_k_sw128(sa + A_BYTES + CV_TERM_B(t) * B_PLANE) + (uint64_t)(k4 * 2);
+                umma_bf16(tmem_d, da, db, idesc, (k4 > 0 || t > 0) ? 1u : 0u);
+              }
             }
+            umma_commit(empty0 + 8u * s);
+            umma_commit(tfull0 + 8u * as);
           }
-          umma_commit(empty0 + 8u * s);
-          umma_commit(tfull0 + 8u * as);
+          __syncwarp();
         }
       }
     }
@@ -163,7 +171,7 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[j] = 0.f;
       for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
-        const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        const uint32_t as = it % NACC, aph = (it / NACC) & 1u;
         bar_wait(tfull0 + 8u * as, aph);
         tmem_fence_after();
 #pragma unroll
@@ -241,9 +249,10 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   unsigned char* smem_al = smem_raw + (smem0 - smem_unaligned);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE);
   const uint32_t full0 = s_u32(bars), empty0 = full0 + 8u * STAGES;
-  const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 16u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  constexpr uint32_t NCOLS = 2u * NT;
+  constexpr uint32_t NACC = CV_NACC(NT);
+  const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 8u * NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
+  constexpr uint32_t NCOLS = NACC * NT;
   const int cpb = p.Ca / 64, U = p.ntaps * cpb;
   const int u0 = 2 * blockIdx.x, u1 = (u0 + 1 < U) ? u0 + 1 : u0;
   const int per = (p.k_blocks + (int)gridDim.z - 1) / (int)gridDim.z;
@@ -257,7 +266,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       bar_init(full0 + 8u * i, 1);
       bar_init(empty0 + 8u * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (int)NACC; ++i) {
       bar_init(tfull0 + 8u * i, 1);
       bar_init(tempty0 + 8u * i, 4);
     }
@@ -298,27 +307,30 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                       // whole warp walks the loop, one elected lane issues
       const uint32_t idesc = idesc_bf16_f32(128, NT, 1, 1);
       for (int i = 0; i < nkb; ++i) {
         const uint32_t s = (uint32_t)i % STAGES, ph = ((uint32_t)i / STAGES) & 1u;
-        const uint32_t as = (uint32_t)i & 1u, aph = ((uint32_t)i >> 1) & 1u;
+        const uint32_t as = (uint32_t)i % NACC, aph = ((uint32_t)i / NACC) & 1u;
         bar_wait(full0 + 8u * s, ph);
         bar_wait(tempty0 + 8u * as, aph ^ 1u);
         tmem_fence_after();
         const uint32_t sa = smem0 + s * STAGE;
         // fresh accumulator per k-block, correction terms first (see conv3x3_fprop_kernel)
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int t = 0; t < 6; ++t) {
+          for (int t = 0; t < 6; ++t) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {                   // 16 pixels (two 8-row atoms = 2048 B) per MMA
-            const uint64_t da = desc_mn_sw128(sa + CV_TERM_A(t) * CV_APLANE + k4 * 2048u, BLK);
-            const uint64_t db = desc_mn_sw128(sa + A_BYTES + CV_TERM_B(t) * B_PLANE + k4 * 2048u, BLK);
-            umma_bf16(tmem_base + as * NT, da, db, idesc, (k4 > 0 || t > 0) ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4) {                 // 16 pixels (two 8-row atoms = 2048 B) per MMA
+              const uint64_t da = desc_mn_sw128(sa + CV_TERM_A(t) * CV_APLANE + k4 * 2048u, BLK);
+              const uint64_t db = desc_mn_sw128(sa + A_BYTES + CV_TERM_B(t) * B_PLANE + k4 * 2048u, BLK);
+              umma_bf16(tmem_base + as * NT, da, db, idesc, (k4 > 0 || t > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(empty0 + 8u * s);
+          umma_commit(tfull0 + 8u * as);
         }
-        umma_commit(empty0 + 8u * s);
-        umma_commit(tfull0 + 8u * as);
+        __syncwarp();
       }
     }
   } else {
@@ -330,7 +342,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j] = 0.f;
     for (int i = 0; i < nkb; ++i) {
-      const uint32_t as = (uint32_t)i & 1u, aph = ((uint32_t)i >> 1) & 1u;
+      const uint32_t as = (uint32_t)i % NACC, aph = ((uint32_t)i / NACC) & 1u;
       bar_wait(tfull0 + 8u * as, aph);
       tmem_fence_after();
 #pragma unroll
@@ -625,10 +637,10 @@ cudaError_t launch_conv_fprop(const ConvTcParams& p0, int sm_count, cudaStream_t
   }
   CUtensorMap tmA, tmB;
   const int NT = (p.Cb % 128 == 0) ? 128 : 64;
-  if (!make_map_act(&tmA, p.a, p.Ca, p.W, p.H, p.N, 3 * p.nsrc, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
   if (!make_map_w(&tmB, p.b, (uint64_t)p.wtaps * p.Ca, (uint64_t)3 * p.Cb, (uint32_t)NT)) return cudaErrorNotSupported;
   const int total = p.m_tiles * (p.Cb / NT) * p.ksplits;
   const int grid = total < sm_count ? total : sm_count;
+  if (!make_map_act(&tmA, p.a, p.Ca, p.W, p.H, p.N, 3 * p.nsrc, p.W, p.bh, p.bn)) return cudaErrorNotSupported;
   eg_count_launch(EG_FAM_CONV, p.ksplits > 1 ? 2 : 1);
   cudaError_t e = NT == 128 ? fprop_launch<128, 2>(tmA, tmB, p, grid, s) : fprop_launch<64, 3>(tmA, tmB, p, grid, s);
   if (e != cudaSuccess || p.ksplits == 1) return e;

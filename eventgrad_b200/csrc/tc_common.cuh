@@ -55,6 +55,19 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// One lane of a fully converged warp (elect.sync).  The MMA warp keeps its control flow warp-uniform and predicates only
+// the issue on this: inside `if (lane == 0)` ptxas cannot prove a single active thread and wraps EVERY tcgen05.mma
+// (a uniform-datapath instruction) in an ELECT / BRA.U.ANY loop with its descriptors rebuilt from vector registers --
+// ~35 cycles of issue per MMA, which capped the tensor pipe at 40 % (N = 64: 32 cycles of work per MMA) / 53-64 % (N = 128).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

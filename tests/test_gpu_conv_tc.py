@@ -25,6 +25,9 @@ CASES = [  # N, H, W, Cin, Cout
     (5, 4, 4, 128, 64),      # 4x4 images, batch not a multiple of the 8-image tile: zero-filled tail
     (3, 8, 8, 64, 64),       # odd number of 2-image tiles
     (40, 32, 32, 64, 64),    # 320 tiles: persistent CTAs walk several tiles, no K split (the small cases above all split K)
+    (40, 16, 16, 128, 128),  # un-split 16-wide, N tile 128
+    (40, 16, 16, 128, 64),   # ... N tile 64, two channel blocks
+    (37, 16, 16, 64, 128),   # ... odd image count, Cin != Cout (dgrad runs the other instantiation)
 ]
 
 
