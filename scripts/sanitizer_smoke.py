@@ -82,6 +82,34 @@ def main():
     p = draw_augment_params(9, 4, "cuda")
     assert torch.allclose(decode_augment(u, 1.0, 0.0, 1.0, p), decode_augment_torch(u, 1.0, 0.0, 1.0, p))
     print("ok augment")
+    # tcgen05 fp32-accuracy convolutions: every kind (forward, dgrad, wgrad; K-split and un-split grids), the fp32 BN
+    # kernels handing bf16 planes over, against cuDNN fp32
+    import torch.nn.functional as F
+    from eventgrad_b200.ops import conv_tc
+    torch.backends.cudnn.allow_tf32 = False
+    cases = [(3, 64, 64, 3, 1, 1, 32), (20, 64, 64, 3, 1, 1, 32), (2, 64, 128, 3, 2, 1, 16), (2, 64, 128, 1, 2, 0, 16),
+             (2, 64, 64, 1, 1, 0, 8), (2, 3, 64, 3, 1, 1, 32), (9, 128, 64, 3, 1, 1, 4)]
+    for (n, ci, co, k, st, pd, hw) in cases:
+        xc = torch.randn(n, ci, hw, hw, device="cuda").contiguous(memory_format=torch.channels_last)
+        wc = (torch.randn(co, ci, k, k, device="cuda") * 0.05).contiguous(memory_format=torch.channels_last)
+        need_dx = ci != 3
+        x1, w1 = xc.clone().requires_grad_(need_dx), wc.clone().requires_grad_(True)
+        y1 = conv_tc.conv2d(x1, w1, None, (st, st), (pd, pd), (1, 1), 1)
+        gy = torch.randn_like(y1)
+        y1.backward(gy)
+        x2, w2 = xc.clone().requires_grad_(need_dx), wc.clone().requires_grad_(True)
+        y2 = F.conv2d(x2, w2, stride=st, padding=pd)
+        y2.backward(gy)
+        assert conv_tc.kind_of(xc, wc, (st, st), (pd, pd), (1, 1), 1) is not None
+        assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-4) and torch.allclose(w1.grad, w2.grad, rtol=1e-4, atol=1e-3)
+        if need_dx:
+            assert torch.allclose(x1.grad, x2.grad, rtol=1e-4, atol=1e-4)
+    from eventgrad_b200.models.resnet import BasicBlock
+    blk = BasicBlock(64, 64).cuda().to(memory_format=torch.channels_last).train()
+    xb = torch.randn(4, 64, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    blk(xb).sum().backward()
+    assert torch.isfinite(xb.grad).all()
+    print("ok conv_tc")
     print("SANITIZER_SMOKE_OK")
 
 
