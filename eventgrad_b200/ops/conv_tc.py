@@ -149,6 +149,42 @@ def wprep(w_oti: torch.Tensor, transposed: bool):
 
 
 KSPLIT = os.environ.get("EGB_CONV_KSPLIT", "1") != "0"
+# weight gradient on a side stream, concurrent with the data gradient of the same layer (two branches inside the step's
+# CUDA graph): both kernels leave SMs idle at small per-GPU batches
+PAR_BWD = os.environ.get("EGB_CONV_PAR_BWD", "1") != "0"     # A/B on B200: 2.74 -> 2.65 ms at batch 32, 10.09 -> 10.06 at 256
+_SIDE = {}
+
+
+class _fork_wgrad:
+    """context: run the enclosed launches on the side stream, ordered after everything enqueued so far on the current
+    stream; `join()` makes the current stream wait for them"""
+
+    def __init__(self, dev, on):
+        self.on = on
+        if on:
+            self.cur = torch.cuda.current_stream(dev)
+            self.side = _SIDE.get(dev)
+            if self.side is None:
+                self.side = _SIDE[dev] = torch.cuda.Stream(dev)
+            self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.cur)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.ctx.__exit__(*a)
+        return False
+
+    def join(self, *tensors):
+        if self.on:
+            self.cur.wait_stream(self.side)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.cur)
 
 
 def fprop(ap, wp, N, H, W, Ca, Cb, taps, nsrc=1, wtaps=9, out=None, OH=None, OW=None, os_=1, op=0, oq=0):
@@ -279,13 +315,24 @@ class _ConvTcFn(torch.autograd.Function):
                 dw = d[:, 0, :27].reshape(Co, 3, 3, 3).permute(0, 3, 1, 2)
         elif kind in ("s1", "p1"):
             taps, dtaps, T = (TAPS_S1, TAPS_S1_DGRAD, 9) if kind == "s1" else (TAPS_1X1, TAPS_1X1, 1)
+            fork = _fork_wgrad(dy.device, PAR_BWD and need_dx and need_dw)
+            if need_dw:
+                k = 3 if kind == "s1" else 1
+                with fork:
+                    dwr = wgrad(xp, gp, N, H, W, Ci, Co, taps, 1)
+                dw = dwr.reshape(Co, k, k, Ci).permute(0, 3, 1, 2)
             if need_dx:
                 dx = fprop(gp, wtp, N, H, W, Co, Ci, dtaps, 1, T).permute(0, 3, 1, 2)
             if need_dw:
-                k = 3 if kind == "s1" else 1
-                dw = wgrad(xp, gp, N, H, W, Ci, Co, taps, 1).reshape(Co, k, k, Ci).permute(0, 3, 1, 2)
+                fork.join(dwr)
         else:
             Ho, Wo = H // 2, W // 2
+            fork = _fork_wgrad(dy.device, PAR_BWD and need_dx and need_dw)
+            if need_dw:
+                k = 3 if kind == "s2" else 1
+                with fork:
+                    dwr = wgrad(xp, gp, N, Ho, Wo, Ci, Co, TAPS_S2 if kind == "s2" else TAPS_1X1, 4)
+                dw = dwr.reshape(Co, k, k, Ci).permute(0, 3, 1, 2)
             if need_dx:
                 if kind == "s2":
                     dxn = torch.empty(N, H, W, Ci, dtype=torch.float32, device=dy.device)
@@ -296,9 +343,7 @@ class _ConvTcFn(torch.autograd.Function):
                     fprop(gp, wtp, N, Ho, Wo, Co, Ci, TAPS_1X1, 1, 1, out=dxn, OH=H, OW=W, os_=2, op=0, oq=0)
                 dx = dxn.permute(0, 3, 1, 2)
             if need_dw:
-                k = 3 if kind == "s2" else 1
-                dw = wgrad(xp, gp, N, Ho, Wo, Ci, Co, TAPS_S2 if kind == "s2" else TAPS_1X1, 4)
-                dw = dw.reshape(Co, k, k, Ci).permute(0, 3, 1, 2)
+                fork.join(dwr)
         return dx, dw, None
 
 
