@@ -47,7 +47,8 @@ using namespace tc;
 // TMEM accumulator ring: all 512 columns (8 accumulators at N tile 64, 4 at 128).  With two, the MMA of k-block i+2
 // has to wait for the drain of k-block i (barrier wake-up + tcgen05.ld + 64-128 adds + arrive); a deeper ring takes that
 // latency off the MMA's critical path.  (Measured neutral at batch 256 -- see the A/B list in profiles/README.md 0a.)
-#define CV_NACC(NT) (512 / (NT))
+#define CV_HV 1   // independent TMEM accumulators per k-block that the K steps alternate between; 2 measured neutral (A/B list)
+#define CV_NACC(NT) (512 / (CV_HV * (NT)))
 #define CV_APLANE 16384u   // one bf16 plane of an operand tile with 128 rows: 128 x 128 B
 
 // the six cross terms (plane of A, plane of B), largest last so that the small corrections are summed first
@@ -70,7 +71,7 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr uint32_t NACC = CV_NACC(NT);
   const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 8u * NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
-  constexpr uint32_t NCOLS = NACC * NT;                    // the whole TMEM: 512 columns
+  constexpr uint32_t NCOLS = NACC * CV_HV * NT;            // the whole TMEM: 512 columns
   const int cpb = p.Ca / 64, num_kb_all = p.ntaps * cpb;
   const int n_tiles = p.Cb / NT;
   const int ksplits = p.ksplits;                           // > 1: few tiles (small batch): split the K loop over CTAs,
@@ -137,7 +138,7 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           bar_wait(full0 + 8u * s, ph);                          // operands have landed
           bar_wait(tempty0 + 8u * as, aph ^ 1u);                 // the accumulator of k-block it-NACC has been drained
           tmem_fence_after();
-          const uint32_t tmem_d = tmem_base + as * NT;
+          const uint32_t tmem_d = tmem_base + as * (CV_HV * NT);
           const uint32_t sa = smem0 + s * STAGE;
           // The tensor core TRUNCATES every accumulation to fp32 (measured: a bias of ~0.5 ulp per MMA towards zero,
           // growing linearly with K).  So each k-block starts a fresh accumulator that the epilogue warps add into
@@ -150,7 +151,8 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = desc_k_sw128(sa + CV_TERM_A(t) * CV_APLANE) + (uint64_t)(k4 * 2);
                 const uint64_t db = desc_k_sw128(sa + A_BYTES + CV_TERM_B(t) * B_PLANE) + (uint64_t)(k4 * 2);
-                umma_bf16(tmem_d, da, db, idesc, (k4 > 0 || t > 0) ? 1u : 0u);
+                // consecutive MMAs alternate between CV_HV accumulators: no MMA waits for the accumulate of its predecessor
+                umma_bf16(tmem_d + (uint32_t)(k4 % CV_HV) * NT, da, db, idesc, (k4 >= CV_HV || t > 0) ? 1u : 0u);
               }
             }
             umma_commit(empty0 + 8u * s);
@@ -176,10 +178,13 @@ conv3x3_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_fence_after();
 #pragma unroll
         for (int cb = 0; cb < NT; cb += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + as * NT + (uint32_t)cb + ((uint32_t)(q * 32) << 16), v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(v[j]);      // fp32 round-to-nearest
+          for (int hv = 0; hv < CV_HV; ++hv) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + as * (CV_HV * NT) + (uint32_t)(hv * NT + cb) + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(v[j]);    // fp32 round-to-nearest
+          }
         }
         tmem_fence_before();
         __syncwarp();
@@ -252,7 +257,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr uint32_t NACC = CV_NACC(NT);
   const uint32_t tfull0 = empty0 + 8u * STAGES, tempty0 = tfull0 + 8u * NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
-  constexpr uint32_t NCOLS = NACC * NT;
+  constexpr uint32_t NCOLS = NACC * CV_HV * NT;
   const int cpb = p.Ca / 64, U = p.ntaps * cpb;
   const int u0 = 2 * blockIdx.x, u1 = (u0 + 1 < U) ? u0 + 1 : u0;
   const int per = (p.k_blocks + (int)gridDim.z - 1) / (int)gridDim.z;
@@ -324,7 +329,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int k4 = 0; k4 < 4; ++k4) {                 // 16 pixels (two 8-row atoms = 2048 B) per MMA
               const uint64_t da = desc_mn_sw128(sa + CV_TERM_A(t) * CV_APLANE + k4 * 2048u, BLK);
               const uint64_t db = desc_mn_sw128(sa + A_BYTES + CV_TERM_B(t) * B_PLANE + k4 * 2048u, BLK);
-              umma_bf16(tmem_base + as * NT, da, db, idesc, (k4 > 0 || t > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + as * (CV_HV * NT) + (uint32_t)(k4 % CV_HV) * NT, da, db, idesc,
+                        (k4 >= CV_HV || t > 0) ? 1u : 0u);
             }
           }
           umma_commit(empty0 + 8u * s);
@@ -347,10 +353,13 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tmem_fence_after();
 #pragma unroll
       for (int cb = 0; cb < NT; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + as * NT + (uint32_t)cb + ((uint32_t)(q * 32) << 16), v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(v[j]);
+        for (int hv = 0; hv < CV_HV; ++hv) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + as * (CV_HV * NT) + (uint32_t)(hv * NT + cb) + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[cb + j] += __uint_as_float(v[j]);
+        }
       }
       tmem_fence_before();
       __syncwarp();
