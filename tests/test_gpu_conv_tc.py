@@ -190,3 +190,37 @@ def test_whole_resnet_runs_on_the_tensor_core_convs_and_is_as_close_to_fp64_as_c
     assert res[True][2] <= 149 + 2 * 28
     assert res[True][0] <= 3 * res[False][0] + 2e-6
     assert res[True][1] <= 2 * res[False][1] + 1e-6
+
+
+def test_bottleneck_resnet50_takes_the_tensor_core_path():
+    """the BottleNeck family (1x1 stride-1 convs up to 2048 channels, 3x3 stride-2 inside the block, 1x1 stride-1 and
+    stride-2 down-samplers): every conv on the tcgen05 kernels, loss and gradients as close to fp64 as cuDNN's"""
+    import copy
+    from eventgrad_b200.models.resnet import make_resnet
+    from eventgrad_b200.ops import ext
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1)
+    m = make_resnet("resnet50", variant="canonical").cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(8, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (8,), device="cuda")
+    m64 = copy.deepcopy(m).double()
+    l64 = F.cross_entropy(m64(x.double()), y)
+    l64.backward()
+    g64 = torch.cat([p.grad.flatten() for p in m64.parameters()])
+    res = {}
+    for on in (True, False):
+        conv_tc.set_enabled(on)
+        m.zero_grad(set_to_none=True)
+        before = dict(ext().launch_counts())["conv"]
+        loss = F.cross_entropy(m(x), y)
+        loss.backward()
+        n = dict(ext().launch_counts())["conv"] - before
+        g = torch.cat([p.grad.flatten() for p in m.parameters()]).double()
+        res[on] = (abs(float(loss) - float(l64)), float((g - g64).norm() / g64.norm()), n)
+    conv_tc.set_enabled(None)
+    print(f"resnet50 vs fp64: |dloss| ours {res[True][0]:.2e} cudnn {res[False][0]:.2e}; grad rel err ours "
+          f"{res[True][1]:.3e} cudnn {res[False][1]:.3e}; conv-family launches {res[True][2]}")
+    n_convs = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.Conv2d))
+    assert res[False][2] == 0 and res[True][2] >= 3 * n_convs
+    assert res[True][0] <= 3 * res[False][0] + 2e-6
+    assert res[True][1] <= 2 * res[False][1] + 1e-6
