@@ -1,4 +1,5 @@
-// eventgrad_b200 -- 3x3 / stride-1 / pad-1 convolution on the 5th-generation tensor cores at fp32 accuracy (sm_100a).
+// eventgrad_b200 -- the convolutions of the ResNet family (3x3 stride 1/2, 1x1 stride 1/2, 3-channel stem: forward, data
+// gradient, weight gradient) on the 5th-generation tensor cores at fp32 accuracy (sm_100a).
 //
 // The reference trains in fp32 (/root/reference/dcifar10/event/event.cpp:259-276 feeds fp32 tensors to
 // torch::nn::Conv2d, resnet.hpp:3-9), and fp32 has no tensor-core path: cuDNN's fp32 kernels are SIMT (74 TFLOP/s
@@ -22,8 +23,12 @@
 //       into fp32 registers (round-to-nearest adds: the tensor core itself truncates) and store the tile at the end.
 //   conv3x3_wgrad_kernel   dW[tap, ci, co] = sum_pix X[pix+tap, ci] * dY[pix, co]            (weight gradient)
 //       both operands are "MN-major" (the contiguous dimension is the channel, K = pixels), expressed with MN-major
-//       SWIZZLE_128B descriptors over the very same TMA boxes; split over pixel ranges, partial sums in a workspace,
-//   conv_wgrad_reduce_kernel   fixed-order (deterministic) sum of the partials + transpose to the OHWI weight layout.
+//       SWIZZLE_128B descriptors over the very same TMA boxes; split over pixel ranges, partial sums in a workspace
+//       (one split: dW is written directly).
+//   conv_wgrad_reduce_kernel   fixed-tree (bitwise reproducible) sum of the partials + transpose to the OHWI layout.
+//   conv_fprop_reduce_kernel   sum of the K-split partial tiles of the forward kernel on small grids (per-GPU batch 32).
+//   Measured (B200, batch 256, 19.3 GFLOP per launch): forward 93-137 us, wgrad 84-163 us = 140-230 TFLOP/s
+//   fp32-equivalent, 1e-7 rms against fp64 (cuDNN fp32: 2-4e-7); A/B history and ncu in profiles/README.md section 0a.
 //   split3_kernel          fp32 -> three bf16 planes (flat; "parity" variant: the four (h%2, w%2) sub-images of the
 //                          input of a STRIDE-2 conv, so that its taps become unit-stride boxes; "stem" variant: the 27
 //                          (tap, rgb) values of the 3-channel stem gathered into one 64-wide K block = a 1x1 conv)

@@ -137,3 +137,26 @@ def test_cpu_and_ineligible_shapes_fall_back_to_library_conv():
     w = torch.randn(64, 64, 3, 3)
     assert not conv_tc.eligible(x, w, (1, 1), (1, 1), (1, 1), 1)
     assert torch.equal(conv_tc.conv2d(x, w, None, (1, 1), (1, 1), (1, 1), 1), F.conv2d(x, w, padding=1))
+
+
+def test_plane_registry_matches_by_identity_and_version_and_dies_with_the_tensor():
+    """ops/conv_tc.py hand-over of bf16 planes from the BN kernels to the convs (CPU tensors suffice for the logic)"""
+    import gc
+    from eventgrad_b200.ops import conv_tc as ct
+    t = torch.zeros(4, 8)
+    planes = torch.zeros(3, t.numel(), dtype=torch.bfloat16)
+    ct.planes_put(t, planes)
+    assert ct.planes_get(t) is planes
+    alias = t.view(4, 8)                       # same memory, another tensor object: not a match
+    assert ct.planes_get(alias) is None
+    t.add_(1)                                  # in-place change: the planes are stale
+    assert ct.planes_get(t) is None
+    ct.planes_put(t, planes)
+    key = t.data_ptr()
+    assert key in ct._PLANES
+    del t, alias
+    gc.collect()
+    assert key not in ct._PLANES               # entry removed by the weakref callback
+    wrong = torch.zeros(2, 8)
+    ct.planes_put(wrong, planes)               # planes of another size are never handed out
+    assert ct.planes_get(wrong) is None
