@@ -160,7 +160,7 @@ class _fork_wgrad:
     stream; `join()` makes the current stream wait for them"""
 
     def __init__(self, dev, on):
-        self.on = on
+        self.on = on = bool(on) and torch.device(dev).type == "cuda"
         if on:
             self.cur = torch.cuda.current_stream(dev)
             self.side = _SIDE.get(dev)
